@@ -1,0 +1,140 @@
+// Shared host-side declarations of the gsi_b200 library (context, device
+// buffers, operators, error plumbing).  Not part of the public ABI: the ABI is
+// include/gsi_b200.h.
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda.h>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+#include <stdexcept>
+#include "../../include/gsi_b200.h"
+
+namespace gsi {
+
+void set_last_error(const std::string& msg);
+
+struct Error : public std::runtime_error {
+    int32_t code;
+    Error(int32_t c, const std::string& m) : std::runtime_error(m), code(c) {}
+};
+
+#define GSI_CUDA(expr)                                                                   \
+    do {                                                                                 \
+        cudaError_t _e = (expr);                                                         \
+        if (_e != cudaSuccess)                                                           \
+            throw gsi::Error(GSI_ERR_CUDA, std::string("CUDA error: ") +                 \
+                                               cudaGetErrorString(_e) + " at " __FILE__ ":" + \
+                                               std::to_string(__LINE__) + " (" #expr ")");   \
+    } while (0)
+
+#define GSI_REQUIRE(cond, code, msg)                       \
+    do {                                                   \
+        if (!(cond)) throw gsi::Error((code), (msg));      \
+    } while (0)
+
+inline int64_t round_up(int64_t x, int64_t m) { return (x + m - 1) / m * m; }
+
+constexpr int kRowPad = 64;        // tall buffers: allocated rows are a multiple of this
+constexpr int kMaxCols = 256;      // widest tall iterate a single GEMM pass handles
+
+// Width bookkeeping of the "tall" layout (row-major, row pitch ld doubles):
+//   lp = 8 * NB   (NB = number of 8-column DMMA blocks, from the instantiated list)
+//   ld = lp + 4   (pitch = 4 mod 8 doubles -> conflict-free B-fragment LDS.64)
+int nb_for_cols(int64_t cols);      // smallest instantiated NB with 8*NB >= cols
+inline int64_t ld_for_cols(int64_t cols) { return 8 * (int64_t)nb_for_cols(cols) + 4; }
+
+}  // namespace gsi
+
+struct gsi_ctx {
+    int device = 0;
+    int rank = 0;
+    int world = 1;
+    int num_sms = 0;
+    cudaStream_t stream = nullptr;
+    void* nccl_comm = nullptr;           // ncclComm_t (dlopen'ed NCCL), world > 1 only
+    // small device scratch reused by the column-step kernels
+    double* scratch = nullptr;           // doubles
+    size_t scratch_doubles = 0;
+    int* dflags = nullptr;               // device int flags [16]
+    // launch counter (kernels launched by this library since last reset)
+    int64_t launches = 0;
+    // optional event pair around the dominant GEMM kernel (bench roofline)
+    double gemm_ms_accum = 0.0;
+    int64_t gemm_launches = 0;
+    double gemm_flops_accum = 0.0;
+    bool time_gemm = false;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+};
+
+struct gsi_buf {
+    gsi_ctx* ctx = nullptr;
+    int32_t layout = GSI_LAYOUT_TALL;
+    int64_t rows = 0, cols = 0;
+    int64_t ld = 0;                      // TALL: row pitch; COLMAJOR: column pitch (doubles)
+    int64_t rows_alloc = 0;              // TALL: padded row count (zero filled)
+    double* d = nullptr;
+    bool owns = true;
+    size_t bytes() const {
+        return layout == GSI_LAYOUT_TALL ? (size_t)rows_alloc * ld * 8 : (size_t)ld * cols * 8;
+    }
+};
+
+enum OpType { OP_DENSE = 0, OP_LOWRANKCOV = 1, OP_KERNELCOV = 2 };
+
+struct gsi_op {
+    gsi_ctx* ctx = nullptr;
+    OpType type = OP_DENSE;
+    int64_t m = 0, n = 0;                // global logical size
+    int64_t row0 = 0, mloc = 0;          // locally owned rows [row0, row0 + mloc)
+    // dense / lowrankcov
+    gsi_buf* A = nullptr;                // COLMAJOR mloc x n (dense) or n x N samples (lowrank)
+    double scale = 1.0;
+    gsi_buf* tmpT = nullptr;             // lowrankcov: N x l intermediate
+    // kernelcov
+    int32_t kind = 0, dim = 0;
+    double sigma2 = 1.0, nugget = 0.0, beta = 1.0;
+    double* ucoords = nullptr;           // [dim][n_pad] scaled coordinates (SoA)
+    int64_t n_pad = 0;
+    std::vector<int64_t> part;           // row partition over ranks: part[r] .. part[r+1]
+};
+
+namespace gsi {
+
+// ---- tall_ops.cu
+void tall_zero(gsi_ctx*, gsi_buf*);
+void tall_copy(gsi_ctx*, const gsi_buf* src, gsi_buf* dst);
+void tall_upload(gsi_buf* b, const double* host, int64_t ldh, int64_t row0, int64_t nrows);
+void tall_download(const gsi_buf* b, double* host, int64_t ldh, int64_t row0, int64_t nrows);
+// out[rows x l2] = Q[rows x l] * M   (M: TALL l x l2 buffer)
+void tall_times_small(gsi_ctx*, const gsi_buf* Q, const gsi_buf* Mtall, gsi_buf* out);
+// small column-major device matrix -> TALL buffer (zero padded)
+void small_cm_to_tall(gsi_ctx*, const double* M, int64_t ldm, int64_t rows, int64_t cols, gsi_buf* T);
+void colmajor_upload(gsi_buf* b, const double* host, int64_t ldh);
+void colmajor_download(const gsi_buf* b, double* host, int64_t ldh);
+
+// ---- kcov_gemm.cu :  W[local rows] = C[rows, :] * X
+void kcov_apply(gsi_op* op, const gsi_buf* X, gsi_buf* W);
+// ---- dense_gemm.cu : W = A X (trans=0) or A' X (trans=1); alpha scaling
+void dense_apply(gsi_ctx*, const gsi_buf* A, int trans, const gsi_buf* X, gsi_buf* W, double alpha);
+// ---- lu.cu : in place, returns unit-lower-trapezoidal L in LAPACK row order
+void lu_L_inplace(gsi_ctx*, gsi_buf* Y, int64_t row0_global, int64_t n_global, const int64_t* part_row0 /* world+1 */);
+// ---- qr.cu : in place thin Q; R (l x l, column-major, device) optional
+void qr_thinQ_inplace(gsi_ctx*, gsi_buf* Y, double* Rdev /* l*l or null */);
+// ---- svd.cu : one-sided Jacobi on l x l column-major device matrix M (overwritten with U),
+//      sigma (device, l) sorted descending, columns of U permuted accordingly
+void svd_small(gsi_ctx*, double* M, int l, double* U, double* sigma);
+// ---- comm.cu
+void comm_allgather(gsi_ctx*, const void* send, void* recv, size_t bytes_per_rank);
+void comm_allreduce_sum(gsi_ctx*, double* buf, size_t count);
+// every rank r contributes counts[r] doubles placed at offsets[r] of `full` (in place ok)
+void comm_allgatherv(gsi_ctx*, double* full, const int64_t* offsets, const int64_t* counts);
+void comm_init(gsi_ctx*, const void* unique_id);
+void comm_destroy(gsi_ctx*);
+void comm_unique_id(void* out128);
+
+inline void count_launch(gsi_ctx* c, int n = 1) { c->launches += n; }
+
+}  // namespace gsi

@@ -1,0 +1,204 @@
+// Dense tall-skinny FP64 GEMM on the tensor cores:
+//   trans = 0:  W[mloc x lp] = alpha * A[mloc x n]  * X[n x lp]      (`A * Omega`, `A * Q`)
+//   trans = 1:  W[n x lp]    = alpha * A[mloc x n]' * X[mloc x lp]   (`A' * Q`, `(Q' * A)'`)
+// A is column-major in HBM (Julia layout) and is read exactly once per pass through
+// tiled TMA (cp.async.bulk.tensor.2d -> UTMALDG) into shared memory; the box is
+// over-fetched by 4 elements along its inner dimension so that the tile pitch is
+// 4 (mod 16) doubles and the DMMA A-fragment LDS.64 pattern is bank-conflict free
+// without swizzling.  X tiles (TALL layout, contiguous rows) arrive by 1-D bulk copy.
+// Math: mma.sync.m8n8k4.f64 (DMMA.8x8x4), 8 x (8*NB) accumulator strip per warp.
+#include "common.cuh"
+#include "ptx.cuh"
+#include "nb_list.h"
+
+namespace gsi {
+
+constexpr int DG_BM = 64;
+constexpr int DG_BK = 32;
+constexpr int DG_PAD = 4;
+constexpr int DG_CONSUMERS = 8;
+constexpr int DG_THREADS = DG_CONSUMERS * 32;   // thread 0 doubles as the TMA producer
+
+struct DenseParams {
+    const double* X;
+    double* W;
+    int64_t out_rows;     // rows of W (mloc for N, n for T)
+    int64_t kdim;         // reduction length (n for N, mloc for T)
+    int64_t ld, ldw;
+    double alpha;
+    int stages;
+};
+
+template <int NB, int TRANS>
+__global__ void __launch_bounds__(DG_THREADS, 1)
+dense_gemm_kernel(const __grid_constant__ CUtensorMap amap, const __grid_constant__ DenseParams p) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    constexpr int ld = NB * 8 + 4;
+    constexpr int a_inner = (TRANS ? DG_BK : DG_BM) + DG_PAD;      // pitch of the A tile (doubles)
+    constexpr int a_outer = TRANS ? DG_BM : DG_BK;
+    constexpr int a_doubles = a_inner * a_outer;
+    constexpr int stage_doubles = DG_BK * ld + a_doubles;
+    double* smem = reinterpret_cast<double*>(smem_raw);
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem + (size_t)p.stages * stage_doubles);
+    uint64_t* empty = full + p.stages;
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int nstages = p.stages;
+    if (tid == 0) {
+        tma_prefetch_desc(&amap);
+        for (int s = 0; s < nstages; ++s) {
+            mbar_init(&full[s], 1);
+            mbar_init(&empty[s], DG_CONSUMERS);
+        }
+        mbar_fence_init();
+    }
+    __syncthreads();
+
+    const int64_t ntiles = (p.out_rows + DG_BM - 1) / DG_BM;
+    const int64_t nkt = (p.kdim + DG_BK - 1) / DG_BK;
+    constexpr uint32_t stage_bytes = (uint32_t)(stage_doubles * sizeof(double));
+
+    const int64_t my_tiles = (ntiles > blockIdx.x) ? (ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+    const int64_t total_it = my_tiles * nkt;
+    const int lookahead = nstages > 2 ? nstages - 2 : 1;
+    auto produce = [&](int64_t nxt) {
+        const int s = (int)(nxt % nstages);
+        const uint32_t ph = (uint32_t)((nxt / nstages) & 1);
+        const int64_t kt = nxt % nkt;
+        const int64_t tile = blockIdx.x + (nxt / nkt) * gridDim.x;
+        mbar_wait(&empty[s], ph ^ 1u);
+        double* xs = smem + (size_t)s * stage_doubles;
+        double* as = xs + DG_BK * ld;
+        mbar_expect_tx(&full[s], stage_bytes);
+        bulk_g2s(xs, p.X + kt * DG_BK * p.ld, DG_BK * ld * 8, &full[s]);
+        if (TRANS) tma_load_2d(as, &amap, (int)(kt * DG_BK), (int)(tile * DG_BM), &full[s]);
+        else       tma_load_2d(as, &amap, (int)(tile * DG_BM), (int)(kt * DG_BK), &full[s]);
+    };
+    if (tid == 0) {
+        for (int64_t i = 0; i < lookahead && i < total_it; ++i) produce(i);
+    }
+
+    const int g = lane >> 2, t = lane & 3;
+    int64_t it = 0;
+    for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        double acc[NB][2];
+#pragma unroll
+        for (int nb = 0; nb < NB; ++nb) { acc[nb][0] = 0.0; acc[nb][1] = 0.0; }
+        for (int64_t kt = 0; kt < nkt; ++kt, ++it) {
+            if (tid == 0 && it + lookahead < total_it) produce(it + lookahead);
+            const int s = (int)(it % nstages);
+            const uint32_t ph = (uint32_t)((it / nstages) & 1);
+            mbar_wait(&full[s], ph);
+            __syncwarp();
+            const double* xs = smem + (size_t)s * stage_doubles;
+            const double* as = xs + DG_BK * ld;
+#pragma unroll 2
+            for (int ks = 0; ks < DG_BK / 4; ++ks) {
+                const int j = ks * 4 + t;
+                const double a = TRANS ? as[(warp * 8 + g) * a_inner + j] : as[j * a_inner + warp * 8 + g];
+                const double* xrow = xs + j * ld + g;
+#pragma unroll
+                for (int nb = 0; nb < NB; ++nb) dmma884(acc[nb][0], acc[nb][1], a, xrow[nb * 8]);
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&empty[s]);
+        }
+        const int64_t row = tile * DG_BM + warp * 8 + g;
+        if (row < p.out_rows) {
+            double* wrow = p.W + row * p.ldw + 2 * t;
+#pragma unroll
+            for (int nb = 0; nb < NB; ++nb) {
+                double2 v;
+                v.x = p.alpha * acc[nb][0];
+                v.y = p.alpha * acc[nb][1];
+                *reinterpret_cast<double2*>(wrow + nb * 8) = v;
+            }
+        }
+    }
+}
+
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
+                                    CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                    CUtensorMapFloatOOBfill);
+
+static PFN_encodeTiled get_encode() {
+    static PFN_encodeTiled fn = nullptr;
+    if (!fn) {
+        void* ptr = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        GSI_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres));
+        GSI_REQUIRE(ptr != nullptr && qres == cudaDriverEntryPointSuccess, GSI_ERR_CUDA,
+                    "cuTensorMapEncodeTiled entry point not available");
+        fn = reinterpret_cast<PFN_encodeTiled>(ptr);
+    }
+    return fn;
+}
+
+static CUtensorMap make_map(const gsi_buf* A, int box_inner, int box_outer) {
+    CUtensorMap map;
+    cuuint64_t dims[2] = {(cuuint64_t)A->rows, (cuuint64_t)A->cols};
+    cuuint64_t strides[1] = {(cuuint64_t)A->ld * sizeof(double)};
+    cuuint32_t box[2] = {(cuuint32_t)box_inner, (cuuint32_t)box_outer};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = get_encode()(&map, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, (void*)A->d, dims, strides, box, estr,
+                              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                              CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    GSI_REQUIRE(r == CUDA_SUCCESS, GSI_ERR_CUDA, "cuTensorMapEncodeTiled failed (code " + std::to_string((int)r) + ")");
+    return map;
+}
+
+template <int NB, int TRANS>
+static void launch_dense(gsi_ctx* ctx, const gsi_buf* A, DenseParams p) {
+    constexpr int ld = NB * 8 + 4;
+    constexpr int a_inner = (TRANS ? DG_BK : DG_BM) + DG_PAD;
+    constexpr int a_outer = TRANS ? DG_BM : DG_BK;
+    constexpr size_t stage_bytes = (size_t)(DG_BK * ld + a_inner * a_outer) * sizeof(double);
+    int stages = (int)((200 * 1024) / stage_bytes);
+    if (stages > 4) stages = 4;
+    if (stages < 2) stages = 2;
+    p.stages = stages;
+    const size_t smem = stages * stage_bytes + 2 * stages * sizeof(uint64_t);
+    CUtensorMap map = make_map(A, a_inner, a_outer);
+    auto kfn = dense_gemm_kernel<NB, TRANS>;
+    GSI_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int occ = 0;
+    GSI_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kfn, DG_THREADS, smem));
+    if (occ < 1) occ = 1;
+    const int64_t ntiles = (p.out_rows + DG_BM - 1) / DG_BM;
+    int64_t grid = (int64_t)ctx->num_sms * occ;
+    if (grid > ntiles) grid = ntiles;
+    if (grid < 1) grid = 1;
+    kfn<<<(unsigned)grid, DG_THREADS, smem, ctx->stream>>>(map, p);
+    GSI_CUDA(cudaGetLastError());
+    count_launch(ctx);
+}
+
+void dense_apply(gsi_ctx* ctx, const gsi_buf* A, int trans, const gsi_buf* X, gsi_buf* W, double alpha) {
+    GSI_REQUIRE(A->layout == GSI_LAYOUT_COLMAJOR, GSI_ERR_INVALID_ARGUMENT, "dense apply: A must be COLMAJOR");
+    GSI_REQUIRE(X->layout == GSI_LAYOUT_TALL && W->layout == GSI_LAYOUT_TALL, GSI_ERR_INVALID_ARGUMENT,
+                "dense apply: X and W must be TALL");
+    GSI_REQUIRE(X->cols == W->cols, GSI_ERR_DIMENSION_MISMATCH, "dense apply: X/W column mismatch");
+    GSI_REQUIRE(X->cols <= kMaxCols, GSI_ERR_UNSUPPORTED, "dense apply: more than 256 columns");
+    const int nb = nb_for_cols(X->cols);
+    GSI_REQUIRE(X->ld == 8 * nb + 4 && W->ld == X->ld, GSI_ERR_INVALID_ARGUMENT, "dense apply: bad pitch");
+    DenseParams p;
+    p.X = X->d; p.W = W->d; p.ld = X->ld; p.ldw = W->ld; p.alpha = alpha; p.stages = 0;
+    if (!trans) {
+        GSI_REQUIRE(X->rows == A->cols, GSI_ERR_DIMENSION_MISMATCH, "dense apply: A*X inner dimension");
+        GSI_REQUIRE(W->rows == A->rows, GSI_ERR_DIMENSION_MISMATCH, "dense apply: A*X output rows");
+        p.out_rows = A->rows; p.kdim = A->cols;
+    } else {
+        GSI_REQUIRE(X->rows == A->rows, GSI_ERR_DIMENSION_MISMATCH, "dense apply: A'*X inner dimension");
+        GSI_REQUIRE(W->rows == A->cols, GSI_ERR_DIMENSION_MISMATCH, "dense apply: A'*X output rows");
+        p.out_rows = A->cols; p.kdim = A->rows;
+    }
+    switch (nb) {
+#define GSI_CASE(N) case N: if (trans) launch_dense<N, 1>(ctx, A, p); else launch_dense<N, 0>(ctx, A, p); break;
+        GSI_NB_LIST(GSI_CASE)
+#undef GSI_CASE
+        default: throw Error(GSI_ERR_UNSUPPORTED, "dense apply: unsupported column-block count");
+    }
+}
+
+}  // namespace gsi

@@ -1,0 +1,221 @@
+// Reference-faithful normaliser:  `F = lu(Y); Q = F.L`
+// (reference src/RandMatFact.jl:60-61,68-69,72-73 -> LAPACK dgetrf).
+//
+// Gaussian elimination with partial pivoting on a tall n x l TALL buffer, in place,
+// with LAPACK's pivot rule (idamax: FIRST row of maximal |value|), physical row
+// interchanges and multiplication by the reciprocal pivot (dgetf2/dgetrf2).  The result
+// is the unit-lower-trapezoidal factor in LAPACK's *permuted* row order -- the reference
+// never un-permutes it.
+//
+// One column = two launches on the context stream (no host sync):
+//   lu_pack      (1 CTA)  reduce the per-CTA pivot candidates of column k, export the
+//                         candidate row and (if owned) row k            -> send buffer
+//   [allgather over ranks when the rows are sharded]
+//   lu_eliminate (grid)   pick the global pivot, move rows k <-> p from the exchanged
+//                         copies (never from memory being rewritten), scale column k,
+//                         rank-1 update of the trailing columns, and -- fused -- the
+//                         arg-max search of column k+1.
+#include "common.cuh"
+
+namespace gsi {
+
+constexpr int LU_THREADS = 256;
+constexpr int LU_WARPS = LU_THREADS / 32;
+
+struct Cand { double val; double idx; };   // idx = global row index (exact in a double)
+
+__device__ __forceinline__ bool cand_better(double v, double i, double bv, double bi) {
+    return (v > bv) || (v == bv && i < bi);
+}
+
+// column-0 search (later columns are searched inside lu_eliminate)
+__global__ void lu_search_kernel(const double* __restrict__ Y, int64_t ld, int64_t nloc, int64_t row0, int col,
+                                 Cand* __restrict__ cand) {
+    double bv = -1.0, bi = 0.0;
+    const int64_t gstart = col;   // rows with global index >= col
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nloc; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t gi = row0 + i;
+        if (gi < gstart) continue;
+        const double v = fabs(Y[i * ld + col]);
+        if (cand_better(v, (double)gi, bv, bi)) { bv = v; bi = (double)gi; }
+    }
+    __shared__ double sv[LU_THREADS], si[LU_THREADS];
+    sv[threadIdx.x] = bv; si[threadIdx.x] = bi;
+    __syncthreads();
+    for (int s = LU_THREADS / 2; s > 0; s >>= 1) {
+        if (threadIdx.x < s) {
+            if (cand_better(sv[threadIdx.x + s], si[threadIdx.x + s], sv[threadIdx.x], si[threadIdx.x])) {
+                sv[threadIdx.x] = sv[threadIdx.x + s]; si[threadIdx.x] = si[threadIdx.x + s];
+            }
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) { cand[blockIdx.x].val = sv[0]; cand[blockIdx.x].idx = si[0]; }
+}
+
+// send layout: [0] = |candidate|, (-1 if this rank has no row >= k), [1] = global row,
+//              [2 .. 2+l) candidate row, [2+l .. 2+2l) row k (only meaningful on its owner)
+__global__ void lu_pack_kernel(const double* __restrict__ Y, int64_t ld, int64_t nloc, int64_t row0, int l, int k,
+                               const Cand* __restrict__ cand, int ncand, double* __restrict__ send) {
+    __shared__ double sv[LU_THREADS], si[LU_THREADS];
+    double bv = -1.0, bi = 0.0;
+    for (int c = threadIdx.x; c < ncand; c += LU_THREADS) {
+        const double v = cand[c].val, i = cand[c].idx;
+        if (v >= 0.0 && cand_better(v, i, bv, bi)) { bv = v; bi = i; }
+    }
+    sv[threadIdx.x] = bv; si[threadIdx.x] = bi;
+    __syncthreads();
+    for (int s = LU_THREADS / 2; s > 0; s >>= 1) {
+        if (threadIdx.x < s) {
+            if (cand_better(sv[threadIdx.x + s], si[threadIdx.x + s], sv[threadIdx.x], si[threadIdx.x])) {
+                sv[threadIdx.x] = sv[threadIdx.x + s]; si[threadIdx.x] = si[threadIdx.x + s];
+            }
+        }
+        __syncthreads();
+    }
+    bv = sv[0]; bi = si[0];
+    if (threadIdx.x == 0) { send[0] = bv; send[1] = bi; }
+    if (bv >= 0.0) {
+        const int64_t li = (int64_t)bi - row0;
+        for (int j = threadIdx.x; j < l; j += LU_THREADS) send[2 + j] = Y[li * ld + j];
+    }
+    const int64_t lk = (int64_t)k - row0;
+    if (lk >= 0 && lk < nloc)
+        for (int j = threadIdx.x; j < l; j += LU_THREADS) send[2 + l + j] = Y[lk * ld + j];
+}
+
+__global__ void __launch_bounds__(LU_THREADS)
+lu_eliminate_kernel(double* __restrict__ Y, int64_t ld, int64_t nloc, int64_t row0, int l, int k,
+                    const double* __restrict__ recv, int world, int owner_k, Cand* __restrict__ cand,
+                    int* __restrict__ flags) {
+    extern __shared__ double sm[];
+    double* prow = sm;            // pivot row (all l columns)
+    double* krow = sm + l;        // previous content of row k
+    __shared__ double s_best[LU_WARPS], s_bidx[LU_WARPS];
+    __shared__ double s_p;
+    const int stride = 2 + 2 * l;
+    if (threadIdx.x == 0) {
+        double bv = -1.0, bi = 0.0;
+        int win = 0;
+        for (int r = 0; r < world; ++r) {
+            const double v = recv[(size_t)r * stride], i = recv[(size_t)r * stride + 1];
+            if (v >= 0.0 && cand_better(v, i, bv, bi)) { bv = v; bi = i; win = r; }
+        }
+        s_p = bi;
+        s_best[0] = (double)win;
+    }
+    __syncthreads();
+    const int win = (int)s_best[0];
+    const int64_t p = (int64_t)s_p;
+    __syncthreads();
+    for (int j = threadIdx.x; j < l; j += LU_THREADS) {
+        prow[j] = recv[(size_t)win * stride + 2 + j];
+        krow[j] = recv[(size_t)owner_k * stride + 2 + l + j];
+    }
+    __syncthreads();
+    const double pivot = prow[k];
+    double rpiv = 0.0;
+    if (pivot == 0.0) {
+        if (blockIdx.x == 0 && threadIdx.x == 0) atomicCAS(&flags[0], 0, k + 1);   // first zero pivot (1-based)
+    } else {
+        rpiv = 1.0 / pivot;
+    }
+    // LAPACK dgetf2: reciprocal scaling when |pivot| >= sfmin, true division otherwise
+    const bool use_recip = fabs(pivot) >= 2.2250738585072014e-308;
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    // row k receives the pivot row (owner only, one CTA)
+    const int64_t lk = (int64_t)k - row0;
+    if (blockIdx.x == 0 && lk >= 0 && lk < nloc && p != k)
+        for (int j = threadIdx.x; j < l; j += LU_THREADS) Y[lk * ld + j] = prow[j];
+
+    double bv = -1.0, bi = 0.0;
+    int64_t lstart = (int64_t)k + 1 - row0;
+    if (lstart < 0) lstart = 0;
+    const int64_t wglobal = (int64_t)blockIdx.x * LU_WARPS + warp;
+    const int64_t wtotal = (int64_t)gridDim.x * LU_WARPS;
+    for (int64_t i = lstart + wglobal; i < nloc; i += wtotal) {
+        const int64_t gi = row0 + i;
+        double* yrow = Y + i * ld;
+        const bool is_p = (gi == p);
+        const double* src = is_p ? krow : yrow;
+        double m;
+        if (pivot == 0.0) m = src[k];
+        else m = use_recip ? src[k] * rpiv : src[k] / pivot;
+        if (is_p) {
+            for (int j = lane; j < k; j += 32) yrow[j] = src[j];     // L part of the moved row
+        }
+        if (lane == 0) yrow[k] = m;
+        for (int j = k + 1 + lane; j < l; j += 32) {
+            const double v = src[j] - m * prow[j];
+            yrow[j] = v;
+            if (j == k + 1) {   // lane 0: candidate for the next column
+                const double a = fabs(v);
+                if (cand_better(a, (double)gi, bv, bi)) { bv = a; bi = (double)gi; }
+            }
+        }
+    }
+    if (lane == 0) { s_best[warp] = bv; s_bidx[warp] = bi; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < LU_WARPS; ++w)
+            if (cand_better(s_best[w], s_bidx[w], bv, bi)) { bv = s_best[w]; bi = s_bidx[w]; }
+        cand[blockIdx.x].val = bv; cand[blockIdx.x].idx = bi;
+    }
+}
+
+// rows with global index < l: zero the U part, unit diagonal
+__global__ void lu_finalize_kernel(double* __restrict__ Y, int64_t ld, int64_t nloc, int64_t row0, int l) {
+    const int64_t gi = blockIdx.x;
+    const int64_t i = gi - row0;
+    if (i < 0 || i >= nloc) return;
+    for (int j = (int)gi + threadIdx.x; j < l; j += blockDim.x) Y[i * ld + j] = (j == gi) ? 1.0 : 0.0;
+}
+
+void lu_L_inplace(gsi_ctx* ctx, gsi_buf* Y, int64_t row0, int64_t n_global, const int64_t* part_row0) {
+    GSI_REQUIRE(Y->layout == GSI_LAYOUT_TALL, GSI_ERR_INVALID_ARGUMENT, "lu: TALL buffer required");
+    const int l = (int)Y->cols;
+    const int64_t nloc = Y->rows;
+    GSI_REQUIRE(n_global >= l, GSI_ERR_UNSUPPORTED, "lu: fewer rows than columns is not supported");
+    const int world = ctx->world;
+    int grid = ctx->num_sms * 4;
+    const int64_t need = (nloc + LU_WARPS - 1) / LU_WARPS;
+    if (grid > need) grid = (int)(need > 0 ? need : 1);
+    const size_t stride = 2 + 2 * (size_t)l;
+    // scratch layout: cand[grid] | send[stride] | recv[world*stride]
+    const size_t need_doubles = 2 * (size_t)grid + stride * (1 + (size_t)world) + 16;
+    GSI_REQUIRE(need_doubles <= ctx->scratch_doubles, GSI_ERR_UNSUPPORTED, "lu: scratch too small");
+    Cand* cand = reinterpret_cast<Cand*>(ctx->scratch);
+    double* send = ctx->scratch + 2 * (size_t)grid;
+    double* recv = (world > 1) ? send + stride : send;
+    GSI_CUDA(cudaMemsetAsync(ctx->dflags, 0, sizeof(int), ctx->stream));
+
+    lu_search_kernel<<<grid, LU_THREADS, 0, ctx->stream>>>(Y->d, Y->ld, nloc, row0, 0, cand);
+    GSI_CUDA(cudaGetLastError());
+    count_launch(ctx);
+    const size_t smem = 2 * (size_t)l * sizeof(double);
+    for (int k = 0; k < l; ++k) {
+        lu_pack_kernel<<<1, LU_THREADS, 0, ctx->stream>>>(Y->d, Y->ld, nloc, row0, l, k, cand, grid, send);
+        GSI_CUDA(cudaGetLastError());
+        int owner_k = 0;
+        if (world > 1) {
+            comm_allgather(ctx, send, recv, stride * sizeof(double));
+            for (int r = 0; r < world; ++r)
+                if (k >= part_row0[r] && k < part_row0[r + 1]) owner_k = r;
+        }
+        lu_eliminate_kernel<<<grid, LU_THREADS, smem, ctx->stream>>>(Y->d, Y->ld, nloc, row0, l, k, recv, world,
+                                                                      owner_k, cand, ctx->dflags);
+        GSI_CUDA(cudaGetLastError());
+        count_launch(ctx, 2);
+    }
+    lu_finalize_kernel<<<l, 64, 0, ctx->stream>>>(Y->d, Y->ld, nloc, row0, l);
+    GSI_CUDA(cudaGetLastError());
+    count_launch(ctx);
+    int flag = 0;
+    GSI_CUDA(cudaMemcpyAsync(&flag, ctx->dflags, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    GSI_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (flag != 0)
+        throw Error(GSI_ERR_SINGULAR, "SingularException(" + std::to_string(flag) + "): exactly zero pivot in lu");
+}
+
+}  // namespace gsi

@@ -1,0 +1,79 @@
+"""CPU-side checks of the C-ABI boundary: the shared library loads, exports every
+symbol include/gsi_b200.h declares, and refuses to run without a GPU (no fallback)."""
+import ctypes
+import os
+import re
+import subprocess
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HEADER = os.path.join(ROOT, "include", "gsi_b200.h")
+LIB = os.path.join(ROOT, "geostatinversion.jl_b200", "lib", "libgsi_b200.so")
+
+
+def declared_symbols():
+    txt = open(HEADER).read()
+    txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
+    return sorted(set(re.findall(r"\b(gsi_[a-z0-9_A-Z]+)\s*\(", txt)))
+
+
+@pytest.fixture(scope="module")
+def lib():
+    if not os.path.exists(LIB):
+        import sys
+        sys.path.insert(0, ROOT)
+        import __graft_entry__
+        __graft_entry__.build()
+    return ctypes.CDLL(LIB)
+
+
+def test_every_declared_symbol_is_exported(lib):
+    syms = declared_symbols()
+    assert len(syms) >= 30
+    for s in syms:
+        assert hasattr(lib, s), f"{s} declared in gsi_b200.h but not exported"
+
+
+def test_binding_table_matches_header():
+    import gsi_b200
+    assert sorted(gsi_b200._lib.SIGNATURES) == declared_symbols()
+
+
+def test_only_gsi_symbols_are_exported():
+    out = subprocess.run(["nm", "-D", "--defined-only", LIB], capture_output=True, text=True).stdout
+    names = [l.split()[-1] for l in out.splitlines() if " T " in l]
+    assert names and all(n.startswith("gsi_") for n in names), names
+
+
+def test_sass_uses_fp64_tensor_cores_and_tma():
+    if not os.path.exists("/usr/local/cuda/bin/cuobjdump"):
+        pytest.skip("cuobjdump not available")
+    sass = subprocess.run(["/usr/local/cuda/bin/cuobjdump", "-sass", LIB], capture_output=True, text=True).stdout
+    assert "DMMA.8x8x4" in sass
+    assert "UTMALDG" in sass and "UBLKCP" in sass
+    assert "sm_100a" in subprocess.run(["/usr/local/cuda/bin/cuobjdump", "-lelf", LIB], capture_output=True,
+                                       text=True).stdout
+
+
+def test_no_cpu_fallback_without_device():
+    import gsi_b200
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    lib_ = gsi_b200._lib.load()
+    assert lib_.gsi_version() == 100
+    with pytest.raises(gsi_b200.NoDeviceError):
+        gsi_b200.Context()
+    import numpy as np
+    with pytest.raises(gsi_b200.NoDeviceError):
+        gsi_b200.randsvd(np.eye(4), 2, 1, 1)
+
+
+def test_product_never_imports_oracle():
+    pkg = os.path.join(ROOT, "geostatinversion.jl_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert "import oracle" not in src and "from oracle" not in src, f

@@ -1,0 +1,154 @@
+"""GPU parity tests of the building blocks, through the C ABI (ctypes), against the
+CPU oracle on identical seeded inputs."""
+import numpy as np
+import pytest
+
+import oracle
+from oracle.gepp_ref import gepp_L_unpermuted
+from gpu_util import gsi, relerr  # noqa: F401
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("shape", [(1, 1), (7, 3), (64, 8), (1000, 60), (4097, 210), (333, 256)])
+def test_tall_roundtrip(gsi, shape):
+    rng = np.random.default_rng(1)
+    a = rng.standard_normal(shape)
+    d = gsi.DeviceMatrix.from_host(gsi.default_context(), a)
+    assert np.array_equal(d.numpy(), a)                 # bit exact
+    assert np.array_equal(d.rows_numpy(shape[0] // 2, shape[0] - shape[0] // 2), a[shape[0] // 2:])
+
+
+@pytest.mark.parametrize("shape", [(5, 3), (1001, 77), (64, 64)])
+def test_colmajor_roundtrip(gsi, shape):
+    rng = np.random.default_rng(2)
+    a = rng.standard_normal(shape)
+    d = gsi.DeviceMatrix.from_host(gsi.default_context(), a, gsi.LAYOUT_COLMAJOR)
+    assert np.array_equal(d.numpy(), a)
+
+
+@pytest.mark.parametrize("m,n,l", [(64, 64, 8), (1000, 1000, 60), (513, 777, 210), (100, 37, 5), (2000, 300, 256),
+                                   (65, 1030, 110)])
+def test_dense_apply(gsi, m, n, l):
+    """`A*X` and `A'*X` (RandMatFact.jl:55,67,70,85) -- DMMA/TMA kernel vs dgemm.
+    Tolerance 1e-13 relative (summation order differs)."""
+    rng = np.random.default_rng(m + n + l)
+    A = rng.standard_normal((m, n))
+    X = rng.standard_normal((n, l))
+    Xt = rng.standard_normal((m, l))
+    op = gsi.DenseMatrix(A)
+    assert op.shape == (m, n) and op.size(1) == m and op.size(2) == n
+    assert relerr(op @ X, A @ X) < 1e-13
+    assert relerr(op.T @ Xt, A.T @ Xt) < 1e-13
+    assert relerr(Xt.T @ op, Xt.T @ A) < 1e-13          # Adjoint * A
+    v = rng.standard_normal(n)
+    assert relerr(op @ v, A @ v) < 1e-13
+
+
+@pytest.mark.parametrize("kind", ["exponential", "gaussian", "powerlaw"])
+@pytest.mark.parametrize("grid,l", [((40, 30), 60), ((14, 12, 10), 210), ((1000,), 8), ((33, 31), 5)])
+def test_kernelcov_apply(gsi, kind, grid, l):
+    """Matrix-free C*X vs the dense oracle materialisation (libm exp/sqrt) -- 1e-12."""
+    rng = np.random.default_rng(len(grid) * 100 + l)
+    coords = oracle.grid_coords(grid)
+    d, n = coords.shape
+    ell = [3.1, 2.7, 2.3][:d]
+    kid = {"exponential": 0, "gaussian": 1, "powerlaw": 2}[kind]
+    C = oracle.kernel_cov_dense(kid, coords, ell, sigma2=1.7, nugget=0.01, beta=0.8)
+    X = rng.standard_normal((n, l))
+    op = gsi.KernelCovMatrix(kind, coords, ell, sigma2=1.7, nugget=0.01, beta=0.8)
+    assert op.shape == (n, n)
+    assert op.T is op
+    Y = op @ X
+    assert relerr(Y, C @ X) < 1e-12
+    assert relerr(X[:, :3].T @ op, X[:, :3].T @ C) < 1e-12
+
+
+def test_kernelcov_unstructured_points(gsi):
+    rng = np.random.default_rng(5)
+    n = 1234
+    coords = rng.uniform(0, 50, size=(3, n))
+    ell = [9.0, 7.0, 5.0]
+    C = oracle.kernel_cov_dense(0, coords, ell)
+    X = rng.standard_normal((n, 27))
+    assert relerr(gsi.KernelCovMatrix("exponential", coords, ell) @ X, C @ X) < 1e-12
+
+
+@pytest.mark.parametrize("m,l", [(50, 7), (200, 60), (64, 64), (1000, 33), (5000, 210), (300, 256)])
+def test_lu_L_matches_reference_rule(gsi, m, l):
+    """`lu(Y).L` unpermuted (RandMatFact.jl:60-61): same pivots as LAPACK dgetrf."""
+    rng = np.random.default_rng(m + l)
+    Y = rng.standard_normal((m, l))
+    L = gsi.lu_L(Y)
+    Lref = oracle.lu_L_unpermuted(Y)
+    assert L.shape == Lref.shape
+    assert np.max(np.abs(L - Lref)) < 1e-11
+    assert np.all(np.diag(L) == 1.0) and np.all(np.triu(L, 1) == 0.0)
+
+
+def test_lu_tie_break_and_singular(gsi):
+    Y = np.array([[1.0, 2.0], [-1.0, 0.5], [1.0, 3.0], [0.5, 1.0]])
+    Lref, piv = gepp_L_unpermuted(Y)
+    assert np.max(np.abs(gsi.lu_L(Y) - Lref)) < 1e-15
+    Z = np.zeros((6, 3))
+    Z[:, 0] = 1.0
+    with pytest.raises(gsi.SingularException):
+        gsi.lu_L(Z)
+
+
+@pytest.mark.parametrize("m,l", [(10, 2), (100, 25), (64, 64), (3000, 210), (777, 110), (500, 256)])
+def test_qr_thinQ(gsi, m, l):
+    rng = np.random.default_rng(m * 3 + l)
+    # graded columns so the conditioning is non trivial
+    Y = rng.standard_normal((m, l)) * (10.0 ** (-8 * np.arange(l) / max(l - 1, 1)))[None, :]
+    Q, R = gsi.qr_thinQ(Y, return_R=True)
+    assert np.max(np.abs(Q.T @ Q - np.eye(l))) < 1e-13
+    assert relerr(Q @ R, Y) < 1e-13
+    assert np.all(np.tril(R, -1) == 0.0)
+    Qo = oracle.randmatfact._qr_pivoted_thinQ(Y)
+    # same range as the reference's pivoted QR (F2)
+    assert np.linalg.norm(Qo - Q @ (Q.T @ Qo), 2) < 1e-6 * 1  # graded: range of tiny columns is ill-conditioned
+    Y2 = rng.standard_normal((m, l))
+    Q2 = gsi.qr_thinQ(Y2)
+    Qo2 = oracle.randmatfact._qr_pivoted_thinQ(Y2)
+    assert np.linalg.norm(Qo2 - Q2 @ (Q2.T @ Qo2), 2) < 1e-12
+
+
+@pytest.mark.parametrize("l", [1, 2, 7, 60, 110, 210, 255, 256])
+def test_svd_small(gsi, l):
+    rng = np.random.default_rng(l)
+    M = np.triu(rng.standard_normal((l, l))) * (10.0 ** (-6 * np.arange(l) / max(l - 1, 1)))[:, None]
+    U, s = gsi.svd_small(M)
+    sref = np.linalg.svd(M, compute_uv=False)
+    assert np.max(np.abs(s - sref) / sref[0]) < 1e-14
+    assert np.max(np.abs(s - sref) / sref) < 1e-9
+    assert np.all(np.diff(s) <= 0)
+    assert np.max(np.abs(U.T @ U - np.eye(l))) < 1e-12
+    # U diag(s) V' = M  =>  U' M has rows of norm s
+    assert np.max(np.abs(np.linalg.norm(U.T @ M, axis=1) - s) / sref[0]) < 1e-13
+
+
+def test_lowrankcov_algebra(gsi):
+    """testrpcga.jl:46-58 on the device operator."""
+    samples = [np.array([-.5, 0., .5]), np.array([1., -1., 0.]), np.array([-.5, 1., -.5])]
+    lrcm = gsi.LowRankCovMatrix(samples)
+    assert lrcm.shape == (3, 3) and lrcm.size(1) == 3
+    with pytest.raises(ValueError):
+        lrcm.size(3)
+    fullcm = np.eye(3) @ lrcm
+    assert np.allclose(fullcm, lrcm @ np.eye(3))
+    assert np.allclose(sum(np.outer(x, x) for x in samples) / 2, fullcm)
+    rng = np.random.default_rng(1)
+    for _ in range(5):
+        x = rng.standard_normal((3, 3))
+        assert np.allclose(fullcm @ x, lrcm @ x)
+        assert np.allclose(fullcm.T @ x, lrcm.T @ x)
+
+
+def test_lowrankcov_vs_oracle(gsi):
+    rng = np.random.default_rng(3)
+    n, N, l = 2500, 100, 50
+    fields = [rng.standard_normal(n) + 3.0 for _ in range(N)]
+    X = rng.standard_normal((n, l))
+    ref = oracle.LowRankCovMatrix(fields) @ X
+    assert relerr(gsi.LowRankCovMatrix(fields) @ X, ref) < 1e-12
