@@ -13,4 +13,5 @@ from .core import (Context, DeviceMatrix, DenseMatrix, LowRankCovMatrix, KernelC
                    set_default_context, as_operator, partition_rows)
 from . import randmatfact as RandMatFact
 from .randmatfact import randsvd, rangefinder, eig_nystrom
+from . import dist
 from .pcga import (getxis, pcgalsqr, pcgadirect, pcga, rga, PCGALowRankMatrix, lu_L, qr_thinQ, svd_small)

@@ -197,7 +197,13 @@ class _Operator:
     def apply(self, X, trans=False):
         """A*X (or A'*X).  X: ndarray or TALL DeviceMatrix holding all operand rows.
         Returns the same kind of object; on a sharded operator only this rank's rows
-        (dense trans: all rows)."""
+        (dense trans: all rows).  Host matrices wider than 256 columns are processed in
+        256-column passes (a TALL device iterate holds at most 256 columns)."""
+        if not isinstance(X, DeviceMatrix):
+            Xh = np.asarray(X, dtype=np.float64)
+            if Xh.ndim == 2 and Xh.shape[1] > 256:
+                return np.concatenate([self.apply(Xh[:, c:c + 256], trans) for c in range(0, Xh.shape[1], 256)],
+                                      axis=1)
         Xd, tmp = _as_tall(self.ctx, X)
         m, n = (self.shape if not self._trans else self.shape[::-1])
         sym = self.symmetric

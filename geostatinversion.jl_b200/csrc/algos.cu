@@ -24,31 +24,45 @@ BufPtr make_buf(gsi_ctx* ctx, int32_t layout, int64_t rows, int64_t cols) {
     } else {
         throw Error(GSI_ERR_INVALID_ARGUMENT, "unknown buffer layout");
     }
-    GSI_CUDA(cudaMalloc(&b->d, b->bytes()));
+    b->d = static_cast<double*>(pool_alloc(ctx, b->bytes()));
     GSI_CUDA(cudaMemsetAsync(b->d, 0, b->bytes(), ctx->stream));
     return b;
 }
 
 void BufDeleter::operator()(gsi_buf* b) const {
     if (!b) return;
-    if (b->owns && b->d) cudaFree(b->d);
+    if (b->owns && b->d) pool_free(b->ctx, b->d, b->bytes());
     delete b;
 }
 
 // ------------------------------------------------------------------ operator application
 static void timed_begin(gsi_ctx* ctx) {
-    if (ctx->time_gemm) GSI_CUDA(cudaEventRecord(ctx->ev0, ctx->stream));
+    if (!ctx->time_gemm) return;
+    if (ctx->ev_used + 2 > ctx->ev_pool.size()) {
+        for (int i = 0; i < 64; ++i) {
+            cudaEvent_t e;
+            GSI_CUDA(cudaEventCreate(&e));
+            ctx->ev_pool.push_back(e);
+        }
+    }
+    GSI_CUDA(cudaEventRecord(ctx->ev_pool[ctx->ev_used], ctx->stream));
 }
 static void timed_end(gsi_ctx* ctx, double flops, int nlaunch) {
-    if (ctx->time_gemm) {
-        GSI_CUDA(cudaEventRecord(ctx->ev1, ctx->stream));
-        GSI_CUDA(cudaEventSynchronize(ctx->ev1));
+    if (!ctx->time_gemm) return;
+    GSI_CUDA(cudaEventRecord(ctx->ev_pool[ctx->ev_used + 1], ctx->stream));
+    ctx->ev_used += 2;
+    ctx->gemm_launches += nlaunch;
+    ctx->gemm_flops_accum += flops;
+}
+// resolve the recorded event pairs into gemm_ms_accum
+void resolve_gemm_timing(gsi_ctx* ctx) {
+    for (size_t i = 0; i + 1 < ctx->ev_used; i += 2) {
+        GSI_CUDA(cudaEventSynchronize(ctx->ev_pool[i + 1]));
         float ms = 0.f;
-        GSI_CUDA(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+        GSI_CUDA(cudaEventElapsedTime(&ms, ctx->ev_pool[i], ctx->ev_pool[i + 1]));
         ctx->gemm_ms_accum += ms;
-        ctx->gemm_launches += nlaunch;
-        ctx->gemm_flops_accum += flops;
     }
+    ctx->ev_used = 0;
 }
 
 // Y = op(A) X.   X: all rows of the operand on this rank.  Output distribution:

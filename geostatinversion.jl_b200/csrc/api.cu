@@ -31,6 +31,49 @@ static int32_t guarded(F&& f) {
     }
 }
 
+// Exact-size free list.  Stream-ordered reuse is safe because every consumer of a block
+// is enqueued on ctx->stream (a block returned to the pool is only handed out to work that
+// is enqueued later on the same stream).
+static std::mutex g_pool_mutex;
+void* pool_alloc(gsi_ctx* ctx, size_t bytes) {
+    {
+        std::lock_guard<std::mutex> lock(g_pool_mutex);
+        for (size_t i = 0; i < ctx->free_blocks.size(); ++i) {
+            if (ctx->free_blocks[i].first == bytes) {
+                void* p = ctx->free_blocks[i].second;
+                ctx->free_blocks.erase(ctx->free_blocks.begin() + i);
+                ctx->cached_bytes -= bytes;
+                return p;
+            }
+        }
+    }
+    void* p = nullptr;
+    cudaError_t e = cudaMalloc(&p, bytes);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        pool_release(ctx);                      // give cached blocks back and retry once
+        GSI_CUDA(cudaMalloc(&p, bytes));
+    }
+    return p;
+}
+void pool_free(gsi_ctx* ctx, void* p, size_t bytes) {
+    if (!p) return;
+    std::lock_guard<std::mutex> lock(g_pool_mutex);
+    const size_t kMaxCached = (size_t)24 << 30;
+    if (ctx->cached_bytes + bytes > kMaxCached || ctx->free_blocks.size() >= 64) {
+        cudaFree(p);
+        return;
+    }
+    ctx->free_blocks.emplace_back(bytes, p);
+    ctx->cached_bytes += bytes;
+}
+void pool_release(gsi_ctx* ctx) {
+    std::lock_guard<std::mutex> lock(g_pool_mutex);
+    for (auto& b : ctx->free_blocks) cudaFree(b.second);
+    ctx->free_blocks.clear();
+    ctx->cached_bytes = 0;
+}
+
 static void use(gsi_ctx* ctx) {
     GSI_REQUIRE(ctx != nullptr, GSI_ERR_INVALID_ARGUMENT, "null context");
     GSI_CUDA(cudaSetDevice(ctx->device));
@@ -88,10 +131,12 @@ GSI_API int32_t gsi_ctx_destroy(gsi_ctx* ctx) {
         cudaSetDevice(ctx->device);
         cudaStreamSynchronize(ctx->stream);
         comm_destroy(ctx);
+        pool_release(ctx);
         if (ctx->scratch) cudaFree(ctx->scratch);
         if (ctx->dflags) cudaFree(ctx->dflags);
         if (ctx->ev0) cudaEventDestroy(ctx->ev0);
         if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+        for (cudaEvent_t e : ctx->ev_pool) cudaEventDestroy(e);
         if (ctx->stream) cudaStreamDestroy(ctx->stream);
         delete ctx;
     });
@@ -117,6 +162,7 @@ GSI_API int32_t gsi_ctx_gemm_timing(gsi_ctx* ctx, int32_t enable, double* ms_out
                                     double* flops_out) {
     return guarded([&] {
         use(ctx);
+        resolve_gemm_timing(ctx);
         if (ms_out) *ms_out = ctx->gemm_ms_accum;
         if (launches_out) *launches_out = ctx->gemm_launches;
         if (flops_out) *flops_out = ctx->gemm_flops_accum;

@@ -67,6 +67,14 @@ struct gsi_ctx {
     double gemm_flops_accum = 0.0;
     bool time_gemm = false;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    // event pairs recorded around operator products while time_gemm is on; resolved
+    // (synchronised + summed) only when the host queries them, so timing adds no sync
+    std::vector<cudaEvent_t> ev_pool;
+    size_t ev_used = 0;
+    // caching device allocator for iterate buffers: cudaMalloc/cudaFree of ~350 MB blocks
+    // cost milliseconds and synchronise the device, so freed blocks are kept for reuse
+    std::vector<std::pair<size_t, void*>> free_blocks;
+    size_t cached_bytes = 0;
 };
 
 struct gsi_buf {
@@ -136,5 +144,9 @@ void comm_destroy(gsi_ctx*);
 void comm_unique_id(void* out128);
 
 inline void count_launch(gsi_ctx* c, int n = 1) { c->launches += n; }
+// ---- api.cu: pooled device memory
+void* pool_alloc(gsi_ctx*, size_t bytes);
+void pool_free(gsi_ctx*, void* p, size_t bytes);
+void pool_release(gsi_ctx*);
 
 }  // namespace gsi

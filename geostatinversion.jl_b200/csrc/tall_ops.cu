@@ -61,8 +61,9 @@ static int64_t stage_rows(int64_t cols) {
 
 struct StageBuf {
     double* d = nullptr;
-    StageBuf() { GSI_CUDA(cudaMalloc(&d, kStageBytes + 32 * 256 * 8)); }
-    ~StageBuf() { if (d) cudaFree(d); }
+    gsi_ctx* ctx;
+    explicit StageBuf(gsi_ctx* c) : ctx(c) { d = static_cast<double*>(pool_alloc(c, kStageBytes + 32 * 256 * 8)); }
+    ~StageBuf() { pool_free(ctx, d, kStageBytes + 32 * 256 * 8); }
 };
 
 void tall_upload(gsi_buf* b, const double* host, int64_t ldh, int64_t row0, int64_t nrows) {
@@ -72,7 +73,7 @@ void tall_upload(gsi_buf* b, const double* host, int64_t ldh, int64_t row0, int6
                 "tall_upload: row range outside buffer");
     GSI_REQUIRE(ldh >= nrows, GSI_ERR_INVALID_ARGUMENT, "tall_upload: leading dimension < rows");
     if (nrows == 0 || b->cols == 0) return;
-    StageBuf st;
+    StageBuf st(ctx);
     const int64_t rb = stage_rows(b->cols);
     for (int64_t r = 0; r < nrows; r += rb) {
         const int64_t cur = (nrows - r < rb) ? nrows - r : rb;
@@ -95,7 +96,7 @@ void tall_download(const gsi_buf* b, double* host, int64_t ldh, int64_t row0, in
                 "tall_download: row range outside buffer");
     GSI_REQUIRE(ldh >= nrows, GSI_ERR_INVALID_ARGUMENT, "tall_download: leading dimension < rows");
     if (nrows == 0 || b->cols == 0) return;
-    StageBuf st;
+    StageBuf st(ctx);
     const int64_t rb = stage_rows(b->cols);
     for (int64_t r = 0; r < nrows; r += rb) {
         const int64_t cur = (nrows - r < rb) ? nrows - r : rb;

@@ -103,7 +103,8 @@ def test_qr_normaliser_is_not_reference(gsi):
     Zqr = gsi.randsvd(A, K, p, 2, Omega=Omega, normaliser=gsi.NORMALISER_QR)
     c = oracle.compare_Z(Zqr, Zref, K)
     sv = np.linalg.svd(A, compute_uv=False)[:K]
-    assert np.max(np.abs(oracle.singvals_from_Z(Zqr, K) - sv) / sv) < 2e-2
+    err = np.abs(oracle.singvals_from_Z(Zqr, K) - sv) / sv
+    assert np.max(err[:10]) < 1e-3 and np.max(err) < 0.5
     assert c["sine"] > 1e-6      # genuinely different subspace
 
 
