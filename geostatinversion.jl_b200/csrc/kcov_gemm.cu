@@ -1,29 +1,35 @@
 // Matrix-free covariance-kernel operator  W[I, :] = C[I, :] * X   (SURVEY.md §8 a8).
 //
-// C[i,j] = sigma2 * k(r2(u_i, u_j)) + nugget * (i == j) is never materialised: every
-// lane generates its one entry of an 8x4 DMMA A-fragment directly in registers
-// (row = lane/4, column = lane%4), multiplies it against the X tile staged in shared
-// memory by 1-D bulk async copies (UBLKCP, mbarrier completion), and accumulates an
-// 8 x (8*NB) output strip per warp in registers with FP64 tensor-core MMAs
-// (mma.sync.m8n8k4.f64 -> DMMA.8x8x4).
+// C[i,j] = sigma2 * k(r2(u_i, u_j)) + nugget * (i == j) is never materialised.  Per
+// 32-point k-tile, the four warps that share a 16-row group generate that group's
+// 16 x 32 block of kernel values ONCE (4 entries per thread, FP64 DFMA/exp) into a
+// double-buffered shared-memory tile laid out for conflict-free DMMA A-fragment loads,
+// synchronise on a 128-thread named barrier, and then each warp multiplies it against its
+// quarter of the X tile with FP64 tensor-core MMAs (mma.sync.m8n8k4.f64 -> DMMA.8x8x4),
+// accumulating a 16 x (8*NB/4) strip in registers.  X tiles (TALL layout, a k-tile is one
+// contiguous chunk) and the scaled coordinates arrive by 1-D bulk async copies (UBLKCP)
+// completing on mbarriers; thread 0 issues them `lookahead` tiles ahead.
 //
-// CTA = 8 warps (64 output rows x all 8*NB columns); thread 0 also issues the bulk
-// copies `lookahead` k-tiles ahead of the math (a 9th producer warp would make ptxas
-// budget registers for 12 warps -> 168/thread, spilling the 27-block accumulator).
+// Why this shape (profiles/r01): a single warp can issue a DMMA only every ~32 cycles
+// while the pipe retires one per 16, and DFMA shares that pipe -- so the SM needs >= 3-4
+// warps per scheduler (16 warps/SM, <= 128 registers each) and every kernel value must be
+// generated exactly once per CTA.  The 8-warp / A-in-registers first version stalled 43 %
+// of samples in `wait` with the DMMA pipe 71 % busy.
+//
+// CTA = 16 warps = 4 row groups (16 rows) x 4 column groups: 64 rows x 8*NB columns.
 // Persistent grid: one CTA per SM (x occupancy), static round-robin over row tiles.
-// X lives in the TALL layout (row pitch ld = 8*NB + 4 doubles), so a BK-row tile is one
-// contiguous chunk and the B-fragment LDS.64 pattern (4 rows x 4 col-octets per
-// half-warp) is bank-conflict free.
 #include "common.cuh"
 #include "ptx.cuh"
 #include "nb_list.h"
 
 namespace gsi {
 
-constexpr int KC_BM = 64;          // rows per CTA tile (8 warps x 8 rows)
+constexpr int KC_BM = 64;          // rows per CTA tile
 constexpr int KC_BK = 32;          // j-points (GEMM K) per pipeline stage
-constexpr int KC_CONSUMERS = 8;
-constexpr int KC_THREADS = KC_CONSUMERS * 32;   // thread 0 doubles as the bulk-copy producer
+constexpr int KC_AP = KC_BK + 4;   // pitch of the generated A tile (4 mod 16 doubles)
+constexpr int KC_WARPS = 16;
+constexpr int KC_THREADS = KC_WARPS * 32;
+constexpr int KC_CG = 4;           // column groups (warps sharing one row group)
 
 struct KcovParams {
     const double* X;       // TALL, all n rows (zero padded), pitch ld
@@ -45,24 +51,34 @@ __device__ __forceinline__ double kern_eval(double r2, double beta) {
     return exp(-beta * log1p(r2));
 }
 
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+    asm volatile("bar.sync %0, %1;" :: "r"(id), "r"(nthreads) : "memory");
+}
+
 template <int NB, int KIND, int DIM>
 __global__ void __launch_bounds__(KC_THREADS, 1) kcov_gemm_kernel(const __grid_constant__ KcovParams p) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    const int ld = NB * 8 + 4;
-    const int stage_doubles = KC_BK * ld + 3 * KC_BK;          // X tile + coordinate tile
+    constexpr int ld = NB * 8 + 4;
+    constexpr int NBW = (NB + KC_CG - 1) / KC_CG;                // n-blocks per warp
+    constexpr int stage_doubles = KC_BK * ld + 3 * KC_BK;        // X tile + coordinate tile
+    constexpr int a_doubles = KC_BM * KC_AP;
     double* smem = reinterpret_cast<double*>(smem_raw);
-    uint64_t* full = reinterpret_cast<uint64_t*>(smem + (size_t)p.stages * stage_doubles);
+    double* a_tiles = smem + (size_t)p.stages * stage_doubles;   // [2][KC_BM][KC_AP]
+    uint64_t* full = reinterpret_cast<uint64_t*>(a_tiles + 2 * a_doubles);
     uint64_t* empty = full + p.stages;
 
     const int tid = threadIdx.x;
     const int warp = tid >> 5;
     const int lane = tid & 31;
     const int nstages = p.stages;
+    const int rg = warp >> 2;                 // row group: rows rg*16 .. rg*16+15 of the tile
+    const int cg = warp & 3;                  // column group
+    const int nb0 = cg * NBW;                 // first n-block of this warp
 
     if (tid == 0) {
         for (int s = 0; s < nstages; ++s) {
             mbar_init(&full[s], 1);
-            mbar_init(&empty[s], KC_CONSUMERS);
+            mbar_init(&empty[s], KC_WARPS);
         }
         mbar_fence_init();
     }
@@ -70,7 +86,7 @@ __global__ void __launch_bounds__(KC_THREADS, 1) kcov_gemm_kernel(const __grid_c
 
     const int64_t ntiles = (p.mloc + KC_BM - 1) / KC_BM;
     const int64_t nkt = (p.n + KC_BK - 1) / KC_BK;
-    const uint32_t stage_bytes = (uint32_t)((KC_BK * ld + DIM * KC_BK) * sizeof(double));
+    constexpr uint32_t stage_bytes = (uint32_t)((KC_BK * ld + DIM * KC_BK) * sizeof(double));
 
     // ---------------- producer (thread 0): streams X / coordinate tiles ----------------------
     const int64_t my_tiles = (ntiles > blockIdx.x) ? (ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
@@ -93,21 +109,25 @@ __global__ void __launch_bounds__(KC_THREADS, 1) kcov_gemm_kernel(const __grid_c
         for (int64_t i = 0; i < lookahead && i < total_it; ++i) produce(i);
     }
 
-    // ---------------- consumer warps -------------------------------------------------------
     const int g = lane >> 2;      // fragment row (A, C) / column (B)
     const int t = lane & 3;       // fragment k index (A, B) / column pair (C)
+    // generation role inside the row group: 128 threads x 4 entries = 16 rows x 32 points
+    const int gtid = tid & 127;                  // thread index within the row group
+    const int grow_in_tile = rg * 16 + (gtid >> 3);
+    const int gj0 = (gtid & 7) * 4;
     int64_t it = 0;
     for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-        const int64_t lrow = tile * KC_BM + warp * 8 + g;              // local output row
-        int64_t grow = p.row0 + lrow;                                  // global point index
-        if (grow > p.n - 1) grow = p.n - 1;                            // tail rows: clamp (never stored)
+        int64_t gpt = p.row0 + tile * KC_BM + grow_in_tile;            // global point of my generated row
+        if (gpt > p.n - 1) gpt = p.n - 1;                              // tail rows: clamp (never stored)
         double ui[DIM];
 #pragma unroll
-        for (int k = 0; k < DIM; ++k) ui[k] = p.u[k * p.n_pad + grow];
+        for (int k = 0; k < DIM; ++k) ui[k] = p.u[k * p.n_pad + gpt];
 
-        double acc[NB][2];
+        double acc[2][NBW][2];
 #pragma unroll
-        for (int nb = 0; nb < NB; ++nb) { acc[nb][0] = 0.0; acc[nb][1] = 0.0; }
+        for (int h = 0; h < 2; ++h)
+#pragma unroll
+            for (int nb = 0; nb < NBW; ++nb) { acc[h][nb][0] = 0.0; acc[h][nb][1] = 0.0; }
 
         for (int64_t kt = 0; kt < nkt; ++kt, ++it) {
             if (tid == 0 && it + lookahead < total_it) produce(it + lookahead);
@@ -117,39 +137,67 @@ __global__ void __launch_bounds__(KC_THREADS, 1) kcov_gemm_kernel(const __grid_c
             __syncwarp();
             const double* xs = smem + (size_t)s * stage_doubles;
             const double* us = xs + KC_BK * ld;
+            double* as = a_tiles + (size_t)(it & 1) * a_doubles;
+            // ---- generate my 4 kernel values of this k-tile
+            {
+                double v[4];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    double r2 = 0.0;
+#pragma unroll
+                    for (int k = 0; k < DIM; ++k) {
+                        const double dk = ui[k] - us[k * KC_BK + gj0 + e];
+                        r2 += dk * dk;
+                    }
+                    v[e] = kern_eval<KIND>(r2, p.beta);
+                }
+                double2* dst = reinterpret_cast<double2*>(as + grow_in_tile * KC_AP + gj0);
+                dst[0] = make_double2(v[0], v[1]);
+                dst[1] = make_double2(v[2], v[3]);
+            }
+            named_bar_sync(1 + rg, 128);          // this row group's 16 x 32 block is complete
+            // ---- tensor-core phase
+            const double* arow0 = as + (rg * 16 + g) * KC_AP + t;
+            const double* arow1 = arow0 + 8 * KC_AP;
 #pragma unroll 2
             for (int ks = 0; ks < KC_BK / 4; ++ks) {
-                const int j = ks * 4 + t;
-                double r2 = 0.0;
+                const double a0 = arow0[ks * 4];
+                const double a1 = arow1[ks * 4];
+                const double* xrow = xs + (ks * 4 + t) * ld + nb0 * 8 + g;
 #pragma unroll
-                for (int k = 0; k < DIM; ++k) {
-                    const double dk = ui[k] - us[k * KC_BK + j];
-                    r2 += dk * dk;
+                for (int nb = 0; nb < NBW; ++nb) {
+                    if (nb0 + nb < NB) {
+                        const double b = xrow[nb * 8];
+                        dmma884(acc[0][nb][0], acc[0][nb][1], a0, b);
+                        dmma884(acc[1][nb][0], acc[1][nb][1], a1, b);
+                    }
                 }
-                const double a = kern_eval<KIND>(r2, p.beta);
-                const double* xrow = xs + j * ld + g;
-#pragma unroll
-                for (int nb = 0; nb < NB; ++nb) dmma884(acc[nb][0], acc[nb][1], a, xrow[nb * 8]);
             }
             __syncwarp();
             if (lane == 0) mbar_arrive(&empty[s]);
         }
 
         // epilogue: W = sigma2 * acc + nugget * X[global row]
-        if (lrow < p.mloc) {
-            double* wrow = p.W + lrow * p.ldw + 2 * t;
-            const double* xg = p.X + (p.row0 + lrow) * p.ld + 2 * t;
 #pragma unroll
-            for (int nb = 0; nb < NB; ++nb) {
-                double2 v;
-                v.x = p.sigma2 * acc[nb][0];
-                v.y = p.sigma2 * acc[nb][1];
-                if (p.nugget != 0.0) {
-                    const double2 xv = *reinterpret_cast<const double2*>(xg + nb * 8);
-                    v.x += p.nugget * xv.x;
-                    v.y += p.nugget * xv.y;
+        for (int h = 0; h < 2; ++h) {
+            const int64_t lrow = tile * KC_BM + rg * 16 + h * 8 + g;
+            if (lrow < p.mloc) {
+                double* wrow = p.W + lrow * p.ldw + nb0 * 8 + 2 * t;
+                const double* xg = p.X + (p.row0 + lrow) * p.ld + nb0 * 8 + 2 * t;
+#pragma unroll
+                for (int nb = 0; nb < NBW; ++nb) {
+                    if (nb0 + nb < NB) {
+                        double2 v;
+                        v.x = p.sigma2 * acc[h][nb][0];
+                        v.y = p.sigma2 * acc[h][nb][1];
+                        if (p.nugget != 0.0) {
+                            const double2 xv = *reinterpret_cast<const double2*>(xg + nb * 8);
+                            v.x += p.nugget * xv.x;
+                            v.y += p.nugget * xv.y;
+                        }
+                        *reinterpret_cast<double2*>(wrow + nb * 8) = v;
+                    }
                 }
-                *reinterpret_cast<double2*>(wrow + nb * 8) = v;
             }
         }
     }
@@ -160,11 +208,12 @@ static void launch_kcov(gsi_ctx* ctx, const KcovParams& p0) {
     KcovParams p = p0;
     const int ld = NB * 8 + 4;
     const size_t stage_bytes = (size_t)(KC_BK * ld + 3 * KC_BK) * sizeof(double);
-    int stages = (int)((200 * 1024) / stage_bytes);
+    const size_t a_bytes = (size_t)2 * KC_BM * KC_AP * sizeof(double);
+    int stages = (int)((224 * 1024 - a_bytes - 256) / stage_bytes);
     if (stages > 4) stages = 4;
     if (stages < 2) stages = 2;
     p.stages = stages;
-    const size_t smem = stages * stage_bytes + 2 * stages * sizeof(uint64_t);
+    const size_t smem = stages * stage_bytes + a_bytes + 2 * stages * sizeof(uint64_t);
     auto kfn = kcov_gemm_kernel<NB, KIND, DIM>;
     GSI_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int occ = 0;

@@ -222,8 +222,10 @@ def _finish_iteration(ctx, Zk, K, X, R, y, results, delta, solver):
     return s
 
 
-def pcgalsqriteration(forwardmodel, s, X, xis, R, y, delta, callback=None, ctx=None, pmap=map, _dev=None):
-    """One PCGA/LSQR iteration (reference src/lsqr.jl:35-63)."""
+def pcgalsqriteration(forwardmodel, s, X, xis, R, y, delta, callback=None, ctx=None, pmap=map, _dev=None,
+                      lsqr_kwargs=None):
+    """One PCGA/LSQR iteration (reference src/lsqr.jl:35-63).  lsqr_kwargs (atol, btol,
+    conlim, maxiter) default to the IterativeSolvers defaults the reference relies on."""
     ctx = ctx or default_context()
     Zk, K, tmp = _dev if _dev is not None else _xis_to_device(ctx, xis)
     try:
@@ -234,7 +236,7 @@ def pcgalsqriteration(forwardmodel, s, X, xis, R, y, delta, callback=None, ctx=N
             callback(s, results[K + 2])
 
         def solver(E, HX, R_, b):
-            return PCGALowRankMatrix(E, HX, R_, ctx).lsqr(b)    # :53-54
+            return PCGALowRankMatrix(E, HX, R_, ctx).lsqr(b, **(lsqr_kwargs or {}))    # :53-54
 
         return _finish_iteration(ctx, Zk, K, X, R, np.asarray(y, dtype=np.float64), results, delta, solver)
     finally:
@@ -256,14 +258,15 @@ def _outer(iteration, s0, maxiters, xtol):
 
 
 def pcgalsqr(forwardmodel, s0, X, xis, R, y, maxiters=5, delta=SQRT_EPS, xtol=1e-6, callback=None, ctx=None,
-             pmap=map):
+             pmap=map, lsqr_kwargs=None):
     """pcgalsqr(forwardmodel, s0, X, xis, R, y; maxiters=5, delta=sqrt(eps), xtol=1e-6)
     (reference src/lsqr.jl:20-33).  Also accepts `callback` (the reference's rga always
     forwards one)."""
     ctx = ctx or default_context()
     dev = _xis_to_device(ctx, xis)
     try:
-        return _outer(lambda s: pcgalsqriteration(forwardmodel, s, X, xis, R, y, delta, callback, ctx, pmap, dev),
+        return _outer(lambda s: pcgalsqriteration(forwardmodel, s, X, xis, R, y, delta, callback, ctx, pmap, dev,
+                                                   lsqr_kwargs),
                       s0, maxiters, xtol)
     finally:
         if dev[2]:
@@ -285,7 +288,9 @@ def pcgadirectiteration(forwardmodel, s, X, xis, R, y, delta, callback, ctx=None
         def solver(E, HX, R_, b):
             nobs = E.shape[0]
             rd, rD = _split_R(R_, nobs)
-            HQH = E @ E.T                                       # sum eta eta'  (:49-53)
+            HQH = np.zeros((nobs, nobs))
+            for i in range(E.shape[1]):                         # ger!(1., etai, etai, HQH)  (:49-53)
+                HQH += np.outer(E[:, i], E[:, i])
             Rm = np.diag(rd) if rd is not None else rD
             bigA = np.block([[HQH + Rm, HX[:, None]], [HX[None, :], np.zeros((1, 1))]])   # :57
             return np.linalg.pinv(bigA, rcond=np.finfo(np.float64).eps * min(bigA.shape)) @ b   # :58

@@ -1,0 +1,238 @@
+"""GPU parity tests of the PCGA / RGA path and of the remaining RandMatFact entry points,
+through the C ABI, against the oracle (reference test/testrpcga.jl, test/testrmf.jl)."""
+import numpy as np
+import pytest
+import scipy.linalg
+
+import oracle
+from gpu_util import gsi, relerr  # noqa: F401
+
+pytestmark = pytest.mark.gpu
+
+
+def makeA(rng, n, m):
+    return rng.standard_normal((n, m)) @ rng.standard_normal((m, n))
+
+
+@pytest.mark.parametrize("n,m", [(10, 2), (10, 5), (100, 5), (100, 10), (100, 25)])
+def test_rangefinder_adaptive(gsi, n, m):
+    # test/testrmf.jl:13-15, and parity with the oracle on identical random vectors
+    rng = np.random.default_rng(1000 * n + m)
+    A = makeA(rng, n, m)
+    Om0, oms = rng.standard_normal((n, 10)), rng.standard_normal((n, n))
+    Q = gsi.rangefinder(A, Omega=Om0, omegas=oms)
+    assert abs(Q.shape[1] - m) <= 1
+    assert np.linalg.norm(A - Q @ Q.T @ A) < 1e-8
+    Qo = oracle.rangefinder_adaptive(A, Om0, oms)
+    assert Q.shape == Qo.shape
+    assert np.linalg.norm(Qo - Q @ (Q.T @ Qo), 2) < 1e-8
+
+
+def test_eig_nystrom_known_answer(gsi):
+    # test/testrmf.jl:21-29: eigenvalues 2, 2 +- sqrt(2)
+    rng = np.random.default_rng(7)
+    A = np.array([[2.0, -1, 0], [-1, 2, -1], [0, -1, 2]])
+    Q = gsi.rangefinder(A, rng=rng)
+    U, Sigmavec = gsi.eig_nystrom(A, Q)
+    expect = np.array([2 + np.sqrt(2), 2.0, 2 - np.sqrt(2)])
+    assert np.linalg.norm(Sigmavec ** 2 - expect) < 1e-8
+    assert np.max(np.abs(U.T @ U - np.eye(3))) < 1e-12
+
+
+def test_eig_nystrom_vs_oracle_and_posdef_error(gsi):
+    rng = np.random.default_rng(3)
+    G = rng.standard_normal((300, 40))
+    A = G @ G.T + 1e-3 * np.eye(300)
+    Q = np.linalg.qr(rng.standard_normal((300, 25)))[0]
+    U, S = gsi.eig_nystrom(A, Q)
+    Uo, So = oracle.eig_nystrom(A, Q)
+    assert np.max(np.abs(S - So) / So) < 1e-10
+    assert np.linalg.norm(Uo - U @ (U.T @ Uo), 2) < 1e-8
+    with pytest.raises(gsi.PosDefException):
+        gsi.eig_nystrom(-A, Q)
+
+
+def test_pcgalowrank_size_and_matvec(gsi):
+    # testrpcga.jl:10-16 and :18-44
+    rng = np.random.default_rng(5)
+    A = gsi.PCGALowRankMatrix([rng.random(20) for _ in range(10)], rng.random(20), np.zeros(20))
+    assert A.size() == (A.size(1), A.size(2)) == (21, 21)
+    with pytest.raises(ValueError):
+        A.size(3)
+    numetas, numobs = 10, 20
+    for noise in (1e16, 0.0):
+        for etagen in ("zeros", "randn"):
+            for hxgen in ("zeros", "randn"):
+                gen = {"zeros": lambda k: np.zeros(k), "randn": lambda k: rng.standard_normal(k)}
+                etas = [gen[etagen](numobs) for _ in range(numetas)]
+                HX = gen[hxgen](numobs)
+                R = noise * np.ones(numobs)
+                lr = gsi.PCGALowRankMatrix(etas, HX, R)
+                big = oracle.PCGALowRankMatrix(etas, HX, R).dense()
+                for i in range(numobs + 1):
+                    x = np.zeros(numobs + 1)
+                    x[i] = 1.0
+                    assert np.allclose(big @ x, lr @ x, rtol=np.sqrt(np.finfo(float).eps), atol=0)
+    # dense R
+    Rd = rng.standard_normal((numobs, numobs))
+    Rd = Rd @ Rd.T
+    etas = [rng.standard_normal(numobs) for _ in range(numetas)]
+    HX = rng.standard_normal(numobs)
+    x = rng.standard_normal(numobs + 1)
+    assert relerr(gsi.PCGALowRankMatrix(etas, HX, Rd) @ x, oracle.PCGALowRankMatrix(etas, HX, Rd) @ x) < 1e-13
+
+
+@pytest.mark.parametrize("nobs,K", [(20, 5), (200, 100), (500, 30)])
+def test_device_lsqr_matches_oracle(gsi, nobs, K):
+    """`IterativeSolvers.lsqr(bigA, b)` (src/lsqr.jl:54) on the device vs the oracle.
+
+    With the package defaults (atol = btol = sqrt(eps)) LSQR stops while the iterate still
+    carries ~1e-8..1e-5 relative error and a one-ulp rounding difference can move the stop
+    by one iteration, so two correct implementations only agree to that level; with tight
+    tolerances the same recurrence agrees to 1e-8 (measured 1e-9..1e-13)."""
+    rng = np.random.default_rng(nobs + K)
+    etas = [rng.standard_normal(nobs) for _ in range(K)]
+    HX = rng.standard_normal(nobs)
+    R = 1e-2 * np.ones(nobs)
+    b = np.concatenate([rng.standard_normal(nobs), [0.0]])
+    A, Ao = gsi.PCGALowRankMatrix(etas, HX, R), oracle.PCGALowRankMatrix(etas, HX, R)
+    xe = np.linalg.lstsq(Ao.dense(), b, rcond=None)[0]
+    x, info = A.lsqr(b, return_info=True)
+    xo, infoo = oracle.lsqr(Ao, b, return_info=True)
+    assert info["istop"] == infoo["istop"] and abs(info["itn"] - infoo["itn"]) <= 1, (info, infoo)
+    assert relerr(x, xe) < 10 * max(relerr(xo, xe), 1e-9)        # same quality as the reference's stop
+    tight = dict(atol=1e-14, btol=1e-14, conlim=1e16)
+    x2, info2 = A.lsqr(b, return_info=True, **tight)
+    xo2, infoo2 = oracle.lsqr(Ao, b, return_info=True, **tight)
+    assert info2["istop"] == infoo2["istop"] and abs(info2["itn"] - infoo2["itn"]) <= 1
+    assert relerr(x2, xo2) < 1e-8
+
+
+def setupsimpletest(rng, M, N, mu):
+    x = rng.standard_normal(N)
+    Q0 = rng.standard_normal((M, N))
+    Q = Q0.T @ Q0
+    sqrtQ = np.real(scipy.linalg.sqrtm(Q))
+    truep = sqrtQ @ rng.standard_normal(N) + mu
+    forward = lambda p: p * x
+    truey = forward(truep)
+    pp = int(round(0.1 * M))
+    Omega = rng.standard_normal((N, M + pp))
+    X = np.full(N, mu)
+    noiselevel = 0.0001
+    R = noiselevel ** 2 * np.ones(N)
+    yobs = truey + noiselevel * rng.standard_normal(N)
+    p0 = np.full(N, mu)
+    return forward, p0, X, Q, Omega, R, yobs, truep, pp
+
+
+TIGHT = dict(atol=1e-15, btol=1e-15, conlim=1e17)
+
+
+@pytest.mark.parametrize("log2N,log2M,mu", [(4, 0, 0.0), (6, 2, 10.0), (8, 3, 0.0), (8, 5, 10.0), (8, 7, 0.0)])
+def test_simpletestpcga(gsi, log2N, log2M, mu):
+    """testrpcga.jl:125-131 end to end on the GPU path (2e-2 vs ground truth, the
+    reference's own bar), plus parity with the oracle run on the SAME xis and the same host
+    forward model.
+
+    Parity bar: ONE iteration from identical s (identical forward-model evaluations) agrees
+    to 1e-8 (direct) / 1e-8 with a converged LSQR.  Full multi-iteration runs re-evaluate
+    finite differences with delta = 1.5e-8 at iterates that differ in the last bits, which
+    re-draws ~1e-8-relative rounding noise in every eta and is then amplified by the
+    noise-free (R = 1e-8) saddle-point solve; they are compared at 1e-3."""
+    N, M = 2 ** log2N, 2 ** log2M
+    rng = np.random.default_rng(100 * log2N + log2M)
+    forward, p0, X, Q, Omega, R, yobs, truep, pp = setupsimpletest(rng, M, N, mu)
+    xis = gsi.getxis(Q, M, pp, Omega=Omega)
+    delta = float(np.sqrt(np.finfo(float).eps))
+    from gsi_b200.pcga import pcgadirectiteration, pcgalsqriteration
+    s1 = pcgadirectiteration(forward, p0, X, xis, R, yobs, delta, lambda s, o: None)
+    s1o = oracle.pcgadirectiteration(forward, p0, X, xis, R, yobs, delta, lambda s, o: None)
+    assert relerr(s1, s1o) < 1e-8
+    popt = gsi.pcgadirect(forward, p0, X, xis, R, yobs)
+    assert np.linalg.norm(popt - truep) / np.linalg.norm(truep) < 2e-2
+    assert relerr(popt, oracle.pcgadirect(forward, p0, X, xis, R, yobs)) < 1e-3
+    if M < N / 6:
+        s1 = pcgalsqriteration(forward, p0, X, xis, R, yobs, delta, lsqr_kwargs=TIGHT)
+        s1o = oracle.pcgalsqriteration(forward, p0, X, xis, R, yobs, delta, lsqr_kwargs=TIGHT)
+        assert relerr(s1, s1o) < 1e-8
+        popt = gsi.pcgalsqr(forward, p0, X, xis, R, yobs)
+        assert np.linalg.norm(popt - truep) / np.linalg.norm(truep) < 2e-2
+        assert relerr(popt, oracle.pcgalsqr(forward, p0, X, xis, R, yobs)) < 1e-3
+
+
+def test_simpletestrga(gsi):
+    # testrpcga.jl:133-138 (default pcgadirect) and the F5 case pcgafunc=pcgalsqr
+    M, N, Nred, mu = 8, 1024, 512, 10.0
+    rng = np.random.default_rng(N)
+    forward, p0, X, Q, Omega, R, yobs, truep, pp = setupsimpletest(rng, M, N, mu)
+    xis = gsi.getxis(Q, M, pp, Omega=Omega)
+    S = rng.standard_normal((Nred, N)) * (1 / np.sqrt(N))
+    calls = []
+    popt = gsi.rga(forward, p0, X, xis, R, yobs, S, callback=lambda s, o: calls.append(len(o)))
+    assert calls and all(c == Nred for c in calls)
+    assert np.linalg.norm(popt - truep) / np.linalg.norm(truep) < 2e-2
+    popt2 = gsi.rga(forward, p0, X, xis, R, yobs, S, pcgafunc=gsi.pcgalsqr)
+    assert np.linalg.norm(popt2 - truep) / np.linalg.norm(truep) < 2e-2
+    pref2 = oracle.rga(forward, p0, X, xis, R, yobs, S, pcgafunc=oracle.pcgalsqr)
+    assert relerr(popt2, pref2) < 1e-3      # default LSQR stop + sketch-GEMM rounding amplified by 1/delta
+
+
+def test_sketch_products(gsi):
+    rng = np.random.default_rng(9)
+    Nred, nobs = 300, 1500
+    S = rng.standard_normal((Nred, nobs)) / np.sqrt(nobs)
+    R = rng.random(nobs) + 0.1
+    from gsi_b200.pcga import _Sketch
+    sk = _Sketch(S, gsi.default_context())
+    assert relerr(sk.cov(R), (S * R[None, :]) @ S.T) < 1e-13
+    V = rng.standard_normal((nobs, 7))
+    assert relerr(sk.apply(V), S @ V) < 1e-13
+    y = rng.standard_normal(nobs)
+    assert relerr(sk.apply(y), S @ y) < 1e-13
+
+
+def test_config2_pcgalsqr_linear_forward_model(gsi):
+    """BASELINE config 2 at reduced grid: 2-D exponential covariance, synthetic linear
+    observations, rank-K prior; declared-linear forward model batched on the device."""
+    rng = np.random.default_rng(2)
+    grid, nobs, K, p = (40, 40), 60, 40, 4
+    coords = oracle.grid_coords(grid)
+    n = coords.shape[1]
+    ell = [12.0, 8.0]
+    C = oracle.kernel_cov_dense(0, coords, ell)
+    Omega = rng.standard_normal((n, K + p))
+    op = gsi.KernelCovMatrix("exponential", coords, ell)
+    xis = gsi.getxis(op, K, p, 3, Omega=Omega)
+    xis_ref = oracle.getxis(C, Omega, K, p, 3)
+    for a, b in zip(xis, xis_ref):
+        assert min(np.linalg.norm(a - b), np.linalg.norm(a + b)) / np.linalg.norm(b) < 1e-8
+    H = rng.standard_normal((nobs, n)) / np.sqrt(n)
+    mu = 2.0
+    Zk = np.stack(xis, axis=1)
+    truth = mu + Zk @ rng.standard_normal(K)
+    noise = 1e-4
+    y = H @ truth + noise * rng.standard_normal(nobs)
+    R = noise ** 2 * np.ones(nobs)
+    X = np.full(n, 1.0)
+    s0 = np.full(n, mu)
+    # (a) host black-box forward model: bit-identical evaluations -> 1e-8 parity
+    fhost = lambda s: H @ s
+    delta = float(np.sqrt(np.finfo(float).eps))
+    from gsi_b200.pcga import pcgalsqriteration
+    # HQH' has rank K < nobs and R = 1e-8: LSQR needs far more than the default nobs+1
+    # iterations to converge in floating point; run both sides to convergence
+    conv = dict(TIGHT, maxiter=20000)
+    s1 = pcgalsqriteration(fhost, s0, X, xis, R, y, delta, lsqr_kwargs=conv)
+    s1o = oracle.pcgalsqriteration(fhost, s0, X, xis, R, y, delta, lsqr_kwargs=conv)
+    assert relerr(s1, s1o) < 1e-8                               # one iteration, converged LSQR
+    sg = gsi.pcgalsqr(fhost, s0, X, xis, R, y)
+    so = oracle.pcgalsqr(fhost, s0, X, xis, R, y)
+    assert relerr(sg, so) < 5e-3                                # default LSQR stop (sqrt(eps)), see test above
+    assert relerr(sg, truth) < 5e-2                             # 60 observations of a 41-dof field
+    # (b) declared linear model: one device GEMM per iteration (rounding differs from the
+    #     host GEMV; finite differences amplify it by 1/delta -> looser tolerance)
+    from gsi_b200.pcga import LinearForwardModel
+    sd = gsi.pcgalsqr(LinearForwardModel(H), s0, X, xis, R, y)
+    assert relerr(sd, truth) < 5e-2
+    assert relerr(sd, so) < 5e-3
