@@ -1,0 +1,167 @@
+# GeostatInversionB200.jl -- `ccall` shim over libgsi_b200.so (include/gsi_b200.h).
+#
+# UNTESTED HERE: Julia is not installed in the build image; this file is a mechanical
+# transcription of the header (the same table the tested Python `ctypes` host uses,
+# geostatinversion.jl_b200/_lib.py).  It keeps the reference's call surface:
+#   RandMatFact.randsvd(A, K, p, q), rangefinder(A, l, q), getxis(Q, numxis, p, q, seed)
+# for A::Matrix{Float64}, A::KernelCovMatrix (new) and A::LowRankCovMatrix.
+module GeostatInversionB200
+
+import Random
+import LinearAlgebra
+
+const LIB = get(ENV, "GSI_B200_LIB", joinpath(@__DIR__, "..", "geostatinversion.jl_b200", "lib", "libgsi_b200.so"))
+
+const GSI_LAYOUT_TALL = Int32(0)
+const GSI_LAYOUT_COLMAJOR = Int32(1)
+const GSI_NORMALISER_LU_REF = Int32(0)
+
+lasterror() = unsafe_string(ccall((:gsi_last_error_string, LIB), Cstring, ()))
+
+function check(status::Int32)
+	status == 0 && return nothing
+	msg = lasterror()
+	status == 2 && throw(DimensionMismatch(msg))
+	status == 3 && throw(LinearAlgebra.SingularException(0))      # lu(...; check=true), RandMatFact.jl:60,68,72
+	status == 4 && throw(LinearAlgebra.PosDefException(0))        # eig_nystrom, RandMatFact.jl:95
+	error(msg)                                                     # incl. "parameter numiterations should be positive, ..."
+end
+
+mutable struct Context
+	h::Ptr{Cvoid}
+	function Context(device::Integer=0; rank::Integer=0, world::Integer=1, uid::Vector{UInt8}=UInt8[])
+		out = Ref{Ptr{Cvoid}}(C_NULL)
+		check(ccall((:gsi_ctx_create, LIB), Int32, (Int32, Int32, Int32, Ptr{UInt8}, Ref{Ptr{Cvoid}}),
+			device, rank, world, world > 1 ? uid : C_NULL, out))
+		ctx = new(out[])
+		finalizer(c->ccall((:gsi_ctx_destroy, LIB), Int32, (Ptr{Cvoid},), c.h), ctx)
+		return ctx
+	end
+end
+
+const defaultctx = Ref{Union{Nothing, Context}}(nothing)
+context() = (defaultctx[] === nothing && (defaultctx[] = Context()); defaultctx[])
+
+mutable struct DeviceMatrix
+	h::Ptr{Cvoid}
+	rows::Int
+	cols::Int
+	function DeviceMatrix(ctx::Context, layout::Int32, rows::Integer, cols::Integer)
+		out = Ref{Ptr{Cvoid}}(C_NULL)
+		check(ccall((:gsi_buf_alloc, LIB), Int32, (Ptr{Cvoid}, Int32, Int64, Int64, Ref{Ptr{Cvoid}}), ctx.h, layout, rows, cols, out))
+		b = new(out[], rows, cols)
+		finalizer(x->ccall((:gsi_buf_free, LIB), Int32, (Ptr{Cvoid},), x.h), b)    # idempotent, never throws
+		return b
+	end
+end
+
+function upload!(b::DeviceMatrix, A::Matrix{Float64})
+	GC.@preserve A check(ccall((:gsi_buf_upload, LIB), Int32, (Ptr{Cvoid}, Ptr{Float64}, Int64), b.h, A, max(1, size(A, 1))))
+	return b
+end
+
+function download(b::DeviceMatrix)
+	A = Matrix{Float64}(undef, b.rows, b.cols)
+	GC.@preserve A check(ccall((:gsi_buf_download, LIB), Int32, (Ptr{Cvoid}, Ptr{Float64}, Int64), b.h, A, max(1, b.rows)))
+	return A
+end
+
+abstract type Operator end
+mutable struct DenseOperator <: Operator; h::Ptr{Cvoid}; buf::DeviceMatrix; ctx::Context; end
+mutable struct KernelCovMatrix <: Operator; h::Ptr{Cvoid}; n::Int; ctx::Context; end
+mutable struct LowRankCovMatrix <: Operator; h::Ptr{Cvoid}; buf::DeviceMatrix; ctx::Context; end
+
+function DenseOperator(A::Matrix{Float64}; ctx::Context=context())
+	buf = upload!(DeviceMatrix(ctx, GSI_LAYOUT_COLMAJOR, size(A)...), A)
+	out = Ref{Ptr{Cvoid}}(C_NULL)
+	check(ccall((:gsi_op_dense, LIB), Int32, (Ptr{Cvoid}, Ptr{Cvoid}, Int64, Int64, Ref{Ptr{Cvoid}}), ctx.h, buf.h, 0, size(A, 1), out))
+	op = DenseOperator(out[], buf, ctx)
+	finalizer(o->ccall((:gsi_op_free, LIB), Int32, (Ptr{Cvoid},), o.h), op)
+	return op
+end
+
+"kind: 0 exponential, 1 gaussian, 2 powerlaw; coords d x n; ell d"
+function KernelCovMatrix(kind::Integer, coords::Matrix{Float64}, ell::Vector{Float64}; sigma2=1.0, nugget=0.0, beta=1.0, ctx::Context=context())
+	d, n = size(coords)
+	out = Ref{Ptr{Cvoid}}(C_NULL)
+	GC.@preserve coords ell check(ccall((:gsi_op_kernelcov, LIB), Int32,
+		(Ptr{Cvoid}, Int32, Int32, Int64, Ptr{Float64}, Ptr{Float64}, Float64, Float64, Float64, Int64, Int64, Ref{Ptr{Cvoid}}),
+		ctx.h, kind, d, n, coords, ell, sigma2, nugget, beta, 0, n, out))
+	op = KernelCovMatrix(out[], n, ctx)
+	finalizer(o->ccall((:gsi_op_free, LIB), Int32, (Ptr{Cvoid},), o.h), op)
+	return op
+end
+
+function LowRankCovMatrix(samples::Vector{Vector{Float64}}; ctx::Context=context())
+	S = reduce(hcat, samples)
+	buf = upload!(DeviceMatrix(ctx, GSI_LAYOUT_COLMAJOR, size(S)...), S)
+	out = Ref{Ptr{Cvoid}}(C_NULL)
+	check(ccall((:gsi_op_lowrankcov, LIB), Int32, (Ptr{Cvoid}, Ptr{Cvoid}, Int32, Ref{Ptr{Cvoid}}), ctx.h, buf.h, 1, out))
+	op = LowRankCovMatrix(out[], buf, ctx)
+	finalizer(o->ccall((:gsi_op_free, LIB), Int32, (Ptr{Cvoid},), o.h), op)
+	return op
+end
+
+function Base.size(op::Operator)
+	m = Ref{Int64}(0); n = Ref{Int64}(0)
+	check(ccall((:gsi_op_size, LIB), Int32, (Ptr{Cvoid}, Ref{Int64}, Ref{Int64}), op.h, m, n))
+	return (Int(m[]), Int(n[]))
+end
+Base.size(op::Operator, i::Int) = (i == 1 || i == 2) ? size(op)[i] : error("there is no $i-th dimension in a $(typeof(op))")
+Base.adjoint(op::Union{KernelCovMatrix, LowRankCovMatrix}) = op      # symmetric (src/lowrank.jl:38-44)
+
+function Base.:*(op::Operator, X::Matrix{Float64})
+	ctx = op.ctx
+	Xd = upload!(DeviceMatrix(ctx, GSI_LAYOUT_TALL, size(X)...), X)
+	Yd = DeviceMatrix(ctx, GSI_LAYOUT_TALL, size(op, 1), size(X, 2))
+	check(ccall((:gsi_op_apply, LIB), Int32, (Ptr{Cvoid}, Int32, Ptr{Cvoid}, Ptr{Cvoid}), op.h, 0, Xd.h, Yd.h))
+	return download(Yd)
+end
+
+module RandMatFact
+import ..GeostatInversionB200: LIB, check, context, Operator, DenseOperator, DeviceMatrix, upload!, download,
+	GSI_LAYOUT_TALL, GSI_NORMALISER_LU_REF
+
+asoperator(A::Operator) = A
+asoperator(A::Matrix{Float64}) = DenseOperator(A)
+
+"randsvd(A, K, p, q) -- reference src/RandMatFact.jl:83-90 (Omega drawn on the host, :54)"
+function randsvd(A, K::Int, p::Int, q::Int)
+	q < 0 && error("parameter numiterations should be positive, but numiterations=$q")
+	op = asoperator(A)
+	n = size(op, 2)
+	Omega = randn(n, K + p)                              # same host RNG stream as the reference
+	Om = upload!(DeviceMatrix(op.ctx, GSI_LAYOUT_TALL, n, K + p), Omega)
+	Z = DeviceMatrix(op.ctx, GSI_LAYOUT_TALL, n, K + p)
+	check(ccall((:gsi_randsvd, LIB), Int32, (Ptr{Cvoid}, Ptr{Cvoid}, Int64, Int64, Int64, Int32, Ptr{Cvoid}, Ptr{Float64}),
+		op.h, Om.h, K, p, q, GSI_NORMALISER_LU_REF, Z.h, C_NULL))
+	return download(Z)
+end
+
+"rangefinder(A, l, numiterations) -- reference src/RandMatFact.jl:50-80"
+function rangefinder(A, l::Int64, numiterations::Int64)
+	numiterations < 0 && error("parameter numiterations should be positive, but numiterations=$numiterations")
+	op = asoperator(A)
+	n = size(op, 2)
+	Om = upload!(DeviceMatrix(op.ctx, GSI_LAYOUT_TALL, n, l), randn(n, l))
+	Q = DeviceMatrix(op.ctx, GSI_LAYOUT_TALL, size(op, 1), l)
+	check(ccall((:gsi_rangefinder_fixed, LIB), Int32, (Ptr{Cvoid}, Ptr{Cvoid}, Int64, Int32, Ptr{Cvoid}), op.h, Om.h, numiterations, GSI_NORMALISER_LU_REF, Q.h))
+	return download(Q)
+end
+end # RandMatFact
+
+function randsvdwithseed(Q, numxis, p, q, seed::Nothing)
+	return RandMatFact.randsvd(Q, numxis, p, q)
+end
+function randsvdwithseed(Q, numxis, p, q, seed::Int)
+	Random.seed!(seed)                                   # src/GeostatInversion.jl:24-27
+	return RandMatFact.randsvd(Q, numxis, p, q)
+end
+
+"getxis(Q, numxis, p, q=3, seed=nothing) -- src/GeostatInversion.jl:63-70; Q::Matrix or any Operator"
+function getxis(Q, numxis::Int, p::Int, q::Int=3, seed=nothing)
+	Z = randsvdwithseed(Q, numxis, p, q, seed)
+	return [Z[:, i] for i = 1:numxis]
+end
+
+end
