@@ -6,7 +6,9 @@
 // over-fetched by 4 elements along its inner dimension so that the tile pitch is
 // 4 (mod 16) doubles and the DMMA A-fragment LDS.64 pattern is bank-conflict free
 // without swizzling.  X tiles (TALL layout, contiguous rows) arrive by 1-D bulk copy.
-// Math: mma.sync.m8n8k4.f64 (DMMA.8x8x4), 8 x (8*NB) accumulator strip per warp.
+// Math: mma.sync.m8n8k4.f64 (DMMA.8x8x4); 16 warps per CTA, each accumulating a
+// 16 x (8*NB/4) strip in registers (one warp issues a DMMA only every ~32 cycles, so the SM
+// needs 3-4 warps per scheduler to keep the FP64 tensor pipe busy -- profiles/r01).
 #include "common.cuh"
 #include "ptx.cuh"
 #include "nb_list.h"
@@ -16,8 +18,9 @@ namespace gsi {
 constexpr int DG_BM = 64;
 constexpr int DG_BK = 32;
 constexpr int DG_PAD = 4;
-constexpr int DG_CONSUMERS = 8;
+constexpr int DG_CONSUMERS = 16;                // 4 row groups (16 rows) x 4 column groups, as in kcov_gemm
 constexpr int DG_THREADS = DG_CONSUMERS * 32;   // thread 0 doubles as the TMA producer
+constexpr int DG_CG = 4;
 
 struct DenseParams {
     const double* X;
@@ -79,11 +82,17 @@ dense_gemm_kernel(const __grid_constant__ CUtensorMap amap, const __grid_constan
     }
 
     const int g = lane >> 2, t = lane & 3;
+    constexpr int NBW = (NB + DG_CG - 1) / DG_CG;
+    const int rg = warp >> 2;
+    const int cg = (warp + rg) & 3;
+    const int nb0 = cg * NBW;
     int64_t it = 0;
     for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-        double acc[NB][2];
+        double acc[2][NBW][2];
 #pragma unroll
-        for (int nb = 0; nb < NB; ++nb) { acc[nb][0] = 0.0; acc[nb][1] = 0.0; }
+        for (int h = 0; h < 2; ++h)
+#pragma unroll
+            for (int nb = 0; nb < NBW; ++nb) { acc[h][nb][0] = 0.0; acc[h][nb][1] = 0.0; }
         for (int64_t kt = 0; kt < nkt; ++kt, ++it) {
             if (tid == 0 && it + lookahead < total_it) produce(it + lookahead);
             const int s = (int)(it % nstages);
@@ -95,23 +104,36 @@ dense_gemm_kernel(const __grid_constant__ CUtensorMap amap, const __grid_constan
 #pragma unroll 2
             for (int ks = 0; ks < DG_BK / 4; ++ks) {
                 const int j = ks * 4 + t;
-                const double a = TRANS ? as[(warp * 8 + g) * a_inner + j] : as[j * a_inner + warp * 8 + g];
-                const double* xrow = xs + j * ld + g;
+                const int r = rg * 16 + g;
+                const double a0 = TRANS ? as[r * a_inner + j] : as[j * a_inner + r];
+                const double a1 = TRANS ? as[(r + 8) * a_inner + j] : as[j * a_inner + r + 8];
+                const double* xrow = xs + j * ld + nb0 * 8 + g;
 #pragma unroll
-                for (int nb = 0; nb < NB; ++nb) dmma884(acc[nb][0], acc[nb][1], a, xrow[nb * 8]);
+                for (int nb = 0; nb < NBW; ++nb) {
+                    if (nb0 + nb < NB) {
+                        const double b = xrow[nb * 8];
+                        dmma884(acc[0][nb][0], acc[0][nb][1], a0, b);
+                        dmma884(acc[1][nb][0], acc[1][nb][1], a1, b);
+                    }
+                }
             }
             __syncwarp();
             if (lane == 0) mbar_arrive(&empty[s]);
         }
-        const int64_t row = tile * DG_BM + warp * 8 + g;
-        if (row < p.out_rows) {
-            double* wrow = p.W + row * p.ldw + 2 * t;
 #pragma unroll
-            for (int nb = 0; nb < NB; ++nb) {
-                double2 v;
-                v.x = p.alpha * acc[nb][0];
-                v.y = p.alpha * acc[nb][1];
-                *reinterpret_cast<double2*>(wrow + nb * 8) = v;
+        for (int h = 0; h < 2; ++h) {
+            const int64_t row = tile * DG_BM + rg * 16 + h * 8 + g;
+            if (row < p.out_rows) {
+                double* wrow = p.W + row * p.ldw + nb0 * 8 + 2 * t;
+#pragma unroll
+                for (int nb = 0; nb < NBW; ++nb) {
+                    if (nb0 + nb < NB) {
+                        double2 v;
+                        v.x = p.alpha * acc[h][nb][0];
+                        v.y = p.alpha * acc[h][nb][1];
+                        *reinterpret_cast<double2*>(wrow + nb * 8) = v;
+                    }
+                }
             }
         }
     }

@@ -72,7 +72,9 @@ __global__ void __launch_bounds__(KC_THREADS, 1) kcov_gemm_kernel(const __grid_c
     const int lane = tid & 31;
     const int nstages = p.stages;
     const int rg = warp >> 2;                 // row group: rows rg*16 .. rg*16+15 of the tile
-    const int cg = warp & 3;                  // column group
+    const int cg = (warp + rg) & 3;           // column group, rotated per row group so that each SM
+                                              // sub-partition (warp % 4) hosts all four column groups
+                                              // (the last group may own fewer n-blocks)
     const int nb0 = cg * NBW;                 // first n-block of this warp
 
     if (tid == 0) {
@@ -102,8 +104,9 @@ __global__ void __launch_bounds__(KC_THREADS, 1) kcov_gemm_kernel(const __grid_c
         mbar_expect_tx(&full[s], stage_bytes);
         bulk_g2s(xs, p.X + kt * KC_BK * p.ld, KC_BK * ld * 8, &full[s]);
 #pragma unroll
+        const int64_t ktn = (kt + 1 == nkt) ? 0 : kt + 1;      // coordinates of the NEXT k-tile ride along
         for (int k = 0; k < DIM; ++k)
-            bulk_g2s(us + k * KC_BK, p.u + k * p.n_pad + kt * KC_BK, KC_BK * 8, &full[s]);
+            bulk_g2s(us + k * KC_BK, p.u + k * p.n_pad + ktn * KC_BK, KC_BK * 8, &full[s]);
     };
     if (tid == 0) {
         for (int64_t i = 0; i < lookahead && i < total_it; ++i) produce(i);
@@ -115,14 +118,41 @@ __global__ void __launch_bounds__(KC_THREADS, 1) kcov_gemm_kernel(const __grid_c
     const int gtid = tid & 127;                  // thread index within the row group
     const int grow_in_tile = rg * 16 + (gtid >> 3);
     const int gj0 = (gtid & 7) * 4;
-    int64_t it = 0;
-    for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-        int64_t gpt = p.row0 + tile * KC_BM + grow_in_tile;            // global point of my generated row
-        if (gpt > p.n - 1) gpt = p.n - 1;                              // tail rows: clamp (never stored)
-        double ui[DIM];
+    auto row_coords = [&](int64_t tile, double (&ui)[DIM]) {
+        int64_t gpt = p.row0 + tile * KC_BM + grow_in_tile;           // global point of my generated row
+        if (gpt > p.n - 1) gpt = p.n - 1;                             // tail rows: clamp (never stored)
 #pragma unroll
         for (int k = 0; k < DIM; ++k) ui[k] = p.u[k * p.n_pad + gpt];
+    };
+    auto gen4 = [&](const double (&ui)[DIM], const double* u0, int64_t ustride, double (&v)[4]) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            double r2 = 0.0;
+#pragma unroll
+            for (int k = 0; k < DIM; ++k) {
+                const double dk = ui[k] - u0[k * ustride + gj0 + e];
+                r2 += dk * dk;
+            }
+            v[e] = kern_eval<KIND>(r2, p.beta);
+        }
+    };
+    auto store4 = [&](double* as, const double (&v)[4]) {
+        double2* dst = reinterpret_cast<double2*>(as + grow_in_tile * KC_AP + gj0);
+        dst[0] = make_double2(v[0], v[1]);
+        dst[1] = make_double2(v[2], v[3]);
+    };
 
+    int64_t it = 0;
+    double ui[DIM];
+    if (blockIdx.x < ntiles) {
+        // prologue: kernel values of (first tile, k-tile 0) straight from global coordinates
+        row_coords(blockIdx.x, ui);
+        double v[4];
+        gen4(ui, p.u, p.n_pad, v);
+        store4(a_tiles, v);
+        named_bar_sync(1 + rg, 128);
+    }
+    for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         double acc[2][NBW][2];
 #pragma unroll
         for (int h = 0; h < 2; ++h)
@@ -136,27 +166,14 @@ __global__ void __launch_bounds__(KC_THREADS, 1) kcov_gemm_kernel(const __grid_c
             mbar_wait(&full[s], ph);
             __syncwarp();
             const double* xs = smem + (size_t)s * stage_doubles;
-            const double* us = xs + KC_BK * ld;
-            double* as = a_tiles + (size_t)(it & 1) * a_doubles;
-            // ---- generate my 4 kernel values of this k-tile
-            {
-                double v[4];
-#pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                    double r2 = 0.0;
-#pragma unroll
-                    for (int k = 0; k < DIM; ++k) {
-                        const double dk = ui[k] - us[k * KC_BK + gj0 + e];
-                        r2 += dk * dk;
-                    }
-                    v[e] = kern_eval<KIND>(r2, p.beta);
-                }
-                double2* dst = reinterpret_cast<double2*>(as + grow_in_tile * KC_AP + gj0);
-                dst[0] = make_double2(v[0], v[1]);
-                dst[1] = make_double2(v[2], v[3]);
-            }
-            named_bar_sync(1 + rg, 128);          // this row group's 16 x 32 block is complete
-            // ---- tensor-core phase
+            const double* us = xs + KC_BK * ld;                       // coordinates of k-tile kt+1 (wraps to 0)
+            const double* as = a_tiles + (size_t)(it & 1) * a_doubles;
+            // ---- kernel values of the NEXT k-tile (independent of the MMAs below: the two
+            //      instruction streams overlap on the shared FP64 pipe)
+            if (kt + 1 == nkt) row_coords(tile + gridDim.x < ntiles ? tile + gridDim.x : tile, ui);
+            double vnext[4];
+            gen4(ui, us, KC_BK, vnext);
+            // ---- tensor-core phase on the current k-tile
             const double* arow0 = as + (rg * 16 + g) * KC_AP + t;
             const double* arow1 = arow0 + 8 * KC_AP;
 #pragma unroll 2
@@ -173,8 +190,10 @@ __global__ void __launch_bounds__(KC_THREADS, 1) kcov_gemm_kernel(const __grid_c
                     }
                 }
             }
+            store4(a_tiles + (size_t)((it + 1) & 1) * a_doubles, vnext);
             __syncwarp();
             if (lane == 0) mbar_arrive(&empty[s]);
+            named_bar_sync(1 + rg, 128);          // next block complete; current block no longer read
         }
 
         // epilogue: W = sigma2 * acc + nugget * X[global row]

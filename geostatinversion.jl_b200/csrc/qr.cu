@@ -17,7 +17,7 @@
 
 namespace gsi {
 
-constexpr int QR_THREADS = 256;
+constexpr int QR_THREADS = 1024;     // 32 warps/SM: the update pass is latency-bound with fewer
 constexpr int QR_WARPS = QR_THREADS / 32;
 constexpr int QR_MAXC = (kMaxCols + 31) / 32;   // column chunks of 32 per lane
 
@@ -32,7 +32,7 @@ __device__ __forceinline__ double block_reduce_sum(double v, double* sh) {
     double r = 0.0;
     if (threadIdx.x < QR_WARPS) r = sh[threadIdx.x];
     if (warp == 0) {
-        for (int o = QR_WARPS / 2; o > 0; o >>= 1) r += __shfl_xor_sync(0xffffffffu, r, o);
+        for (int o = 16; o > 0; o >>= 1) r += __shfl_xor_sync(0xffffffffu, r, o);
         if (lane == 0) sh[0] = r;
     }
     __syncthreads();
@@ -79,13 +79,14 @@ qr_dots0_kernel(const double* __restrict__ Y, int64_t ld, int64_t n, int l, doub
     store_partials(psum, 0, l, sm, partial + (size_t)blockIdx.x * l);
 }
 
+constexpr int QH_THREADS = 256;      // single-CTA scalar kernels
 // Householder scalars of column k + row-k update.  tw[j] = tau * w_j for j > k.
-__global__ void __launch_bounds__(QR_THREADS)
+__global__ void __launch_bounds__(QH_THREADS)
 qr_house_kernel(double* __restrict__ Y, int64_t ld, int l, int k, const double* __restrict__ partial, int nparts,
                 double* __restrict__ tw, double* __restrict__ taus, QrScal* __restrict__ scal) {
     __shared__ double s_g[kMaxCols];
     __shared__ double s_tau, s_scale;
-    for (int j = k + threadIdx.x; j < l; j += QR_THREADS) {
+    for (int j = k + threadIdx.x; j < l; j += QH_THREADS) {
         double s = 0.0;
         for (int b = 0; b < nparts; ++b) s += partial[(size_t)b * l + j];
         s_g[j] = s;
@@ -108,7 +109,7 @@ qr_house_kernel(double* __restrict__ Y, int64_t ld, int l, int k, const double* 
     }
     __syncthreads();
     const double tau = s_tau, scale = s_scale;
-    for (int j = k + 1 + threadIdx.x; j < l; j += QR_THREADS) {
+    for (int j = k + 1 + threadIdx.x; j < l; j += QH_THREADS) {
         const double ykj = Y[(int64_t)k * ld + j];
         const double w = ykj + scale * s_g[j];      // v' * Y[:, j]   (v_k = 1)
         const double t = tau * w;
@@ -159,11 +160,11 @@ qr_update_kernel(double* __restrict__ Y, int64_t ld, int64_t n, int l, int k, co
 // ---- explicit Q (dorg2r), backwards ---------------------------------------------------------
 // Step k: d_j = sum_{i>k} v_k[i] Q[i,j] arrives in `partial` (rows i > k; accumulated by the
 // previous org_update, i.e. of step k+1).
-__global__ void __launch_bounds__(QR_THREADS)
+__global__ void __launch_bounds__(QH_THREADS)
 org_house_kernel(double* __restrict__ Y, int64_t ld, int l, int k, const double* __restrict__ partial, int nparts,
                  const double* __restrict__ taus, double* __restrict__ tw) {
     const double tau = taus[k];
-    for (int j = k + 1 + threadIdx.x; j < l; j += QR_THREADS) {
+    for (int j = k + 1 + threadIdx.x; j < l; j += QH_THREADS) {
         double d = 0.0;
         for (int b = 0; b < nparts; ++b) d += partial[(size_t)b * l + j];
         const double qkj = Y[(int64_t)k * ld + j];
@@ -173,7 +174,7 @@ org_house_kernel(double* __restrict__ Y, int64_t ld, int l, int k, const double*
         tw[j] = t;
     }
     // column k above the diagonal holds R entries: Q has zeros there
-    for (int i = threadIdx.x; i < k; i += QR_THREADS) Y[(int64_t)i * ld + k] = 0.0;
+    for (int i = threadIdx.x; i < k; i += QH_THREADS) Y[(int64_t)i * ld + k] = 0.0;
     if (threadIdx.x == 0) Y[(int64_t)k * ld + k] = 1.0 - tau;
 }
 
@@ -241,12 +242,15 @@ void qr_thinQ_inplace(gsi_ctx* ctx, gsi_buf* Y, double* Rdev) {
     const size_t smem_upd = ((size_t)QR_WARPS * l + l) * sizeof(double);
     const size_t smem_dot = (size_t)QR_WARPS * l * sizeof(double);
     cudaStream_t st = ctx->stream;
+    GSI_CUDA(cudaFuncSetAttribute(qr_update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_upd));
+    GSI_CUDA(cudaFuncSetAttribute(org_update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_upd));
+    GSI_CUDA(cudaFuncSetAttribute(qr_dots0_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_dot));
 
     qr_dots0_kernel<<<grid, QR_THREADS, smem_dot, st>>>(Y->d, Y->ld, n, l, partial);
     GSI_CUDA(cudaGetLastError());
     count_launch(ctx);
     for (int k = 0; k < l; ++k) {
-        qr_house_kernel<<<1, QR_THREADS, 0, st>>>(Y->d, Y->ld, l, k, partial, grid, tw, taus, scal);
+        qr_house_kernel<<<1, QH_THREADS, 0, st>>>(Y->d, Y->ld, l, k, partial, grid, tw, taus, scal);
         qr_update_kernel<<<grid, QR_THREADS, smem_upd, st>>>(Y->d, Y->ld, n, l, k, tw, scal, partial);
         GSI_CUDA(cudaGetLastError());
         count_launch(ctx, 2);
@@ -259,9 +263,9 @@ void qr_thinQ_inplace(gsi_ctx* ctx, gsi_buf* Y, double* Rdev) {
     // ---- form Q in place, k = l-1 .. 0
     GSI_CUDA(cudaMemsetAsync(partial, 0, (size_t)grid * l * sizeof(double), st));
     for (int k = l - 1; k >= 0; --k) {
-        org_house_kernel<<<1, QR_THREADS, 0, st>>>(Y->d, Y->ld, l, k, partial, grid, taus, tw);
+        org_house_kernel<<<1, QH_THREADS, 0, st>>>(Y->d, Y->ld, l, k, partial, grid, taus, tw);
         org_update_kernel<<<grid, QR_THREADS, smem_upd, st>>>(Y->d, Y->ld, n, l, k, tw, taus, partial);
-        if (k > 0) org_rowterm_kernel<<<1, QR_THREADS, 0, st>>>(Y->d, Y->ld, l, k, partial);
+        if (k > 0) org_rowterm_kernel<<<1, QH_THREADS, 0, st>>>(Y->d, Y->ld, l, k, partial);
         GSI_CUDA(cudaGetLastError());
         count_launch(ctx, k > 0 ? 3 : 2);
     }
