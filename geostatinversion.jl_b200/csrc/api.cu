@@ -330,11 +330,13 @@ GSI_API int32_t gsi_op_kernelcov(gsi_ctx* ctx, int32_t kind, int32_t d, int64_t 
         op->m = op->n = n; op->row0 = row0; op->mloc = mloc;
         op->sigma2 = sigma2; op->nugget = nugget; op->beta = beta;
         op->n_pad = round_up(n, kRowPad);
-        // scaled SoA coordinates u[k][j] = x_j[k] / ell[k]; padding repeats the last point
+        // scaled SoA coordinates u[k][j] = x_j[k] / ell[k]; padding repeats the last point.
+        // Gaussian: an extra 1/sqrt(2) folds the factor 1/2 of exp(-r2/2) into r2.
+        const double pre = (kind == GSI_KERNEL_GAUSSIAN) ? 0.70710678118654752440 : 1.0;
         std::vector<double> u((size_t)3 * op->n_pad, 0.0);
         for (int k = 0; k < d; ++k) {
             double* uk = u.data() + (size_t)k * op->n_pad;
-            for (int64_t j = 0; j < n; ++j) uk[j] = coords[j * d + k] / ell[k];
+            for (int64_t j = 0; j < n; ++j) uk[j] = (coords[j * d + k] / ell[k]) * pre;
             for (int64_t j = n; j < op->n_pad; ++j) uk[j] = uk[n - 1];
         }
         GSI_CUDA(cudaMalloc(&op->ucoords, u.size() * sizeof(double)));

@@ -4,7 +4,8 @@
 // 32-point k-tile, the four warps that share a 16-row group generate that group's
 // 16 x 32 block of kernel values ONCE (4 entries per thread, FP64 DFMA/exp) into a
 // double-buffered shared-memory tile laid out for conflict-free DMMA A-fragment loads,
-// synchronise on a 128-thread named barrier, and then each warp multiplies it against its
+// synchronise through a per-row-group mbarrier (arrive after publishing, wait right before
+// the first read, so stragglers are covered by the next tile's generation work), and then each warp multiplies it against its
 // quarter of the X tile with FP64 tensor-core MMAs (mma.sync.m8n8k4.f64 -> DMMA.8x8x4),
 // accumulating a 16 x (8*NB/4) strip in registers.  X tiles (TALL layout, a k-tile is one
 // contiguous chunk) and the scaled coordinates arrive by 1-D bulk async copies (UBLKCP)
@@ -17,7 +18,8 @@
 // of samples in `wait` with the DMMA pipe 71 % busy.
 //
 // CTA = 16 warps = 4 row groups (16 rows) x 4 column groups: 64 rows x 8*NB columns.
-// Persistent grid: one CTA per SM (x occupancy), static round-robin over row tiles.
+// Persistent grid: one CTA per SM (x occupancy), static schedule: full rounds of 64-row
+// tiles plus one tail round at 16-row-group granularity (see the schedule comment below).
 #include "common.cuh"
 #include "ptx.cuh"
 #include "nb_list.h"
@@ -44,10 +46,61 @@ struct KcovParams {
     int stages;
 };
 
+// 2^(j/64), j = 0..63, correctly rounded (generated with 200-bit arithmetic)
+__constant__ double kExp2Table[64] = {
+    0x1.0000000000000p+0, 0x1.02c9a3e778061p+0, 0x1.059b0d3158574p+0, 0x1.0874518759bc8p+0,
+    0x1.0b5586cf9890fp+0, 0x1.0e3ec32d3d1a2p+0, 0x1.11301d0125b51p+0, 0x1.1429aaea92de0p+0,
+    0x1.172b83c7d517bp+0, 0x1.1a35beb6fcb75p+0, 0x1.1d4873168b9aap+0, 0x1.2063b88628cd6p+0,
+    0x1.2387a6e756238p+0, 0x1.26b4565e27cddp+0, 0x1.29e9df51fdee1p+0, 0x1.2d285a6e4030bp+0,
+    0x1.306fe0a31b715p+0, 0x1.33c08b26416ffp+0, 0x1.371a7373aa9cbp+0, 0x1.3a7db34e59ff7p+0,
+    0x1.3dea64c123422p+0, 0x1.4160a21f72e2ap+0, 0x1.44e086061892dp+0, 0x1.486a2b5c13cd0p+0,
+    0x1.4bfdad5362a27p+0, 0x1.4f9b2769d2ca7p+0, 0x1.5342b569d4f82p+0, 0x1.56f4736b527dap+0,
+    0x1.5ab07dd485429p+0, 0x1.5e76f15ad2148p+0, 0x1.6247eb03a5585p+0, 0x1.6623882552225p+0,
+    0x1.6a09e667f3bcdp+0, 0x1.6dfb23c651a2fp+0, 0x1.71f75e8ec5f74p+0, 0x1.75feb564267c9p+0,
+    0x1.7a11473eb0187p+0, 0x1.7e2f336cf4e62p+0, 0x1.82589994cce13p+0, 0x1.868d99b4492edp+0,
+    0x1.8ace5422aa0dbp+0, 0x1.8f1ae99157736p+0, 0x1.93737b0cdc5e5p+0, 0x1.97d829fde4e50p+0,
+    0x1.9c49182a3f090p+0, 0x1.a0c667b5de565p+0, 0x1.a5503b23e255dp+0, 0x1.a9e6b5579fdbfp+0,
+    0x1.ae89f995ad3adp+0, 0x1.b33a2b84f15fbp+0, 0x1.b7f76f2fb5e47p+0, 0x1.bcc1e904bc1d2p+0,
+    0x1.c199bdd85529cp+0, 0x1.c67f12e57d14bp+0, 0x1.cb720dcef9069p+0, 0x1.d072d4a07897cp+0,
+    0x1.d5818dcfba487p+0, 0x1.da9e603db3285p+0, 0x1.dfc97337b9b5fp+0, 0x1.e502ee78b3ff6p+0,
+    0x1.ea4afa2a490dap+0, 0x1.efa1bee615a27p+0, 0x1.f50765b6e4540p+0, 0x1.fa7c1819e90d8p+0,
+};
+
+// exp(-y) for y >= 0 with a 64-entry table and a degree-5 polynomial: 10 FP64 pipe
+// instructions instead of the ~17 of the library exp() -- the kernel generation shares the
+// FP64 pipe with the DMMAs (a register-resident DMMA loop drops from 37.1 to 31.6 TF/s when
+// one library-exp Gaussian value is generated per 28 DMMAs, tools/mma_lds_peak.cu), so
+// every DFMA removed here is tensor throughput.  Max error 2 ulp (library exp: 1 ulp);
+// results below 2^-1000 are flushed to zero.  `tab` is the table staged in shared memory.
+__device__ __forceinline__ double fast_exp_neg(double y, const double* __restrict__ tab) {
+    const double L = 92.33248261689366;                    // 64 / ln 2
+    const double MAGIC = 6755399441055744.0;               // 1.5 * 2^52: round-to-nearest integer trick
+    const double LN2_64_HI = 0x1.62e42fef80000p-7;         // ln2/64, 34 significant bits (k * HI exact)
+    const double LN2_64_LO = 0x1.1cf79abc9e3b4p-42;
+    const double t = fma(y, -L, MAGIC);
+    const int k = __double2loint(t);                       // k = round(-y * 64 / ln2) <= 0
+    const double kf = t - MAGIC;
+    double r = fma(kf, -LN2_64_HI, -y);
+    r = fma(kf, -LN2_64_LO, r);                            // |r| <= ln2/128
+    double p = 1.0 / 120.0;
+    p = fma(p, r, 1.0 / 24.0);
+    p = fma(p, r, 1.0 / 6.0);
+    p = fma(p, r, 0.5);
+    p = fma(p, r, 1.0);
+    p = fma(p, r, 1.0);
+    const double v = tab[k & 63] * p;                      // in [1/2 .. 2)
+    const int e = k >> 6;                                  // floor(k / 64) <= 0
+    const int hi = __double2hiint(v) + (e << 20);
+    const double res = __hiloint2double(hi, __double2loint(v));
+    return e < -1000 ? 0.0 : res;
+}
+
+// kind-specific value from r2.  For the Gaussian kernel the coordinates handed to the
+// kernel are pre-scaled by 1/sqrt(2) so that r2 already carries the factor 1/2.
 template <int KIND>
-__device__ __forceinline__ double kern_eval(double r2, double beta) {
-    if (KIND == GSI_KERNEL_EXPONENTIAL) return exp(-sqrt(r2));
-    if (KIND == GSI_KERNEL_GAUSSIAN) return exp(-0.5 * r2);
+__device__ __forceinline__ double kern_eval(double r2, double beta, const double* __restrict__ tab) {
+    if (KIND == GSI_KERNEL_EXPONENTIAL) return fast_exp_neg(sqrt(r2), tab);
+    if (KIND == GSI_KERNEL_GAUSSIAN) return fast_exp_neg(r2, tab);
     return exp(-beta * log1p(r2));
 }
 
@@ -66,6 +119,8 @@ __global__ void __launch_bounds__(KC_THREADS, 1) kcov_gemm_kernel(const __grid_c
     double* a_tiles = smem + (size_t)p.stages * stage_doubles;   // [2][KC_BM][KC_AP]
     uint64_t* full = reinterpret_cast<uint64_t*>(a_tiles + 2 * a_doubles);
     uint64_t* empty = full + p.stages;
+    uint64_t* abar = empty + p.stages;                            // one per row group, 4 warp arrivals
+    double* etab = reinterpret_cast<double*>(abar + 4);           // 2^(j/64) table for fast_exp_neg
 
     const int tid = threadIdx.x;
     const int warp = tid >> 5;
@@ -77,22 +132,42 @@ __global__ void __launch_bounds__(KC_THREADS, 1) kcov_gemm_kernel(const __grid_c
                                               // (the last group may own fewer n-blocks)
     const int nb0 = cg * NBW;                 // first n-block of this warp
 
+    if (tid < 64) etab[tid] = kExp2Table[tid];
     if (tid == 0) {
         for (int s = 0; s < nstages; ++s) {
             mbar_init(&full[s], 1);
             mbar_init(&empty[s], KC_WARPS);
         }
+        for (int r = 0; r < 4; ++r) mbar_init(&abar[r], KC_CG);
         mbar_fence_init();
     }
     __syncthreads();
 
-    const int64_t ntiles = (p.mloc + KC_BM - 1) / KC_BM;
+    // Work schedule.  Full rounds: CTA b takes the 64-row tile (round*grid + b), i.e. four
+    // consecutive 16-row groups.  The remaining (< 4*grid) row groups form ONE tail round
+    // spread over all CTAs, q = ceil(remaining/grid) groups each: a CTA with a single
+    // active row group finishes its k-sweep in ~0.4 of a full tile's time (its 4 warps are
+    // DMMA-issue-bound, not pipe-bound), which removes most of the wave-quantisation tail.
+    const int64_t total_rg = (p.mloc + 15) / 16;
+    const int64_t per_round = (int64_t)gridDim.x * 4;
+    const int64_t full_rounds = total_rg / per_round;
+    const int64_t remaining = total_rg - full_rounds * per_round;
+    const int64_t q_tail = (remaining + gridDim.x - 1) / gridDim.x;          // 0..4
+    const bool has_tail = remaining > 0 && (int64_t)blockIdx.x * q_tail < remaining;
+    const int64_t my_rounds = full_rounds + (has_tail ? 1 : 0);
+    // first row group and number of active row groups of my round j
+    auto round_base = [&](int64_t j, int& nact) -> int64_t {
+        if (j < full_rounds) { nact = 4; return (j * gridDim.x + blockIdx.x) * 4; }
+        const int64_t b0 = (int64_t)blockIdx.x * q_tail;
+        const int64_t left = remaining - b0;
+        nact = (int)(left < q_tail ? left : q_tail);
+        return full_rounds * per_round + b0;
+    };
     const int64_t nkt = (p.n + KC_BK - 1) / KC_BK;
     constexpr uint32_t stage_bytes = (uint32_t)((KC_BK * ld + DIM * KC_BK) * sizeof(double));
 
     // ---------------- producer (thread 0): streams X / coordinate tiles ----------------------
-    const int64_t my_tiles = (ntiles > blockIdx.x) ? (ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
-    const int64_t total_it = my_tiles * nkt;
+    const int64_t total_it = my_rounds * nkt;
     const int lookahead = nstages > 2 ? nstages - 2 : 1;
     auto produce = [&](int64_t nxt) {
         const int s = (int)(nxt % nstages);
@@ -118,8 +193,8 @@ __global__ void __launch_bounds__(KC_THREADS, 1) kcov_gemm_kernel(const __grid_c
     const int gtid = tid & 127;                  // thread index within the row group
     const int grow_in_tile = rg * 16 + (gtid >> 3);
     const int gj0 = (gtid & 7) * 4;
-    auto row_coords = [&](int64_t tile, double (&ui)[DIM]) {
-        int64_t gpt = p.row0 + tile * KC_BM + grow_in_tile;           // global point of my generated row
+    auto row_coords = [&](int64_t base_rg, double (&ui)[DIM]) {
+        int64_t gpt = p.row0 + base_rg * 16 + grow_in_tile;           // global point of my generated row
         if (gpt > p.n - 1) gpt = p.n - 1;                             // tail rows: clamp (never stored)
 #pragma unroll
         for (int k = 0; k < DIM; ++k) ui[k] = p.u[k * p.n_pad + gpt];
@@ -133,7 +208,7 @@ __global__ void __launch_bounds__(KC_THREADS, 1) kcov_gemm_kernel(const __grid_c
                 const double dk = ui[k] - u0[k * ustride + gj0 + e];
                 r2 += dk * dk;
             }
-            v[e] = kern_eval<KIND>(r2, p.beta);
+            v[e] = kern_eval<KIND>(r2, p.beta, etab);
         }
     };
     auto store4 = [&](double* as, const double (&v)[4]) {
@@ -144,15 +219,26 @@ __global__ void __launch_bounds__(KC_THREADS, 1) kcov_gemm_kernel(const __grid_c
 
     int64_t it = 0;
     double ui[DIM];
-    if (blockIdx.x < ntiles) {
-        // prologue: kernel values of (first tile, k-tile 0) straight from global coordinates
-        row_coords(blockIdx.x, ui);
-        double v[4];
-        gen4(ui, p.u, p.n_pad, v);
-        store4(a_tiles, v);
-        named_bar_sync(1 + rg, 128);
+    int nact = 0, nact_next = 0;
+    int64_t base_rg = 0;
+    if (my_rounds > 0) {
+        // prologue: kernel values of (first round, k-tile 0) straight from global coordinates
+        base_rg = round_base(0, nact);
+        row_coords(base_rg, ui);
+        if (rg < nact) {
+            double v[4];
+            gen4(ui, p.u, p.n_pad, v);
+            store4(a_tiles, v);
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&abar[rg]);
     }
-    for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    for (int64_t round = 0; round < my_rounds; ++round) {
+        if (round > 0) base_rg = round_base(round, nact);
+        const bool active = rg < nact;                                // warp-uniform
+        int64_t base_next = base_rg;
+        nact_next = 0;
+        if (round + 1 < my_rounds) base_next = round_base(round + 1, nact_next);
         double acc[2][NBW][2];
 #pragma unroll
         for (int h = 0; h < 2; ++h)
@@ -170,37 +256,56 @@ __global__ void __launch_bounds__(KC_THREADS, 1) kcov_gemm_kernel(const __grid_c
             const double* as = a_tiles + (size_t)(it & 1) * a_doubles;
             // ---- kernel values of the NEXT k-tile (independent of the MMAs below: the two
             //      instruction streams overlap on the shared FP64 pipe)
-            if (kt + 1 == nkt) row_coords(tile + gridDim.x < ntiles ? tile + gridDim.x : tile, ui);
-            double vnext[4];
-            gen4(ui, us, KC_BK, vnext);
-            // ---- tensor-core phase on the current k-tile
+            const bool last_kt = (kt + 1 == nkt);
+            if (last_kt) row_coords(base_next, ui);
+            const bool gen_next = last_kt ? (rg < nact_next) : active;
+            double* anext = a_tiles + (size_t)((it + 1) & 1) * a_doubles + grow_in_tile * KC_AP + gj0;
+            // ---- tensor-core phase on the current k-tile: wait until the whole row group has
+            //      published this block (and has stopped reading the other buffer)
+            mbar_wait(&abar[rg], (uint32_t)(it & 1));
+            __syncwarp();
             const double* arow0 = as + (rg * 16 + g) * KC_AP + t;
             const double* arow1 = arow0 + 8 * KC_AP;
-#pragma unroll 2
-            for (int ks = 0; ks < KC_BK / 4; ++ks) {
-                const double a0 = arow0[ks * 4];
-                const double a1 = arow1[ks * 4];
-                const double* xrow = xs + (ks * 4 + t) * ld + nb0 * 8 + g;
 #pragma unroll
-                for (int nb = 0; nb < NBW; ++nb) {
-                    if (nb0 + nb < NB) {
-                        const double b = xrow[nb * 8];
-                        dmma884(acc[0][nb][0], acc[0][nb][1], a0, b);
-                        dmma884(acc[1][nb][0], acc[1][nb][1], a1, b);
+            for (int ks = 0; ks < KC_BK / 4; ++ks) {
+                // one kernel value of the NEXT k-tile every second k-step: a single exp chain
+                // is live at a time and its DFMAs interleave with this step's DMMAs
+                if ((ks & 1) == 0 && gen_next) {
+                    const int e = ks >> 1;
+                    double r2 = 0.0;
+#pragma unroll
+                    for (int k = 0; k < DIM; ++k) {
+                        const double dk = ui[k] - us[k * KC_BK + gj0 + e];
+                        r2 += dk * dk;
+                    }
+                    anext[e] = kern_eval<KIND>(r2, p.beta, etab);
+                }
+                if (active) {
+                    const double a0 = arow0[ks * 4];
+                    const double a1 = arow1[ks * 4];
+                    const double* xrow = xs + (ks * 4 + t) * ld + nb0 * 8 + g;
+#pragma unroll
+                    for (int nb = 0; nb < NBW; ++nb) {
+                        if (nb0 + nb < NB) {
+                            const double b = xrow[nb * 8];
+                            dmma884(acc[0][nb][0], acc[0][nb][1], a0, b);
+                            dmma884(acc[1][nb][0], acc[1][nb][1], a1, b);
+                        }
                     }
                 }
             }
-            store4(a_tiles + (size_t)((it + 1) & 1) * a_doubles, vnext);
             __syncwarp();
-            if (lane == 0) mbar_arrive(&empty[s]);
-            named_bar_sync(1 + rg, 128);          // next block complete; current block no longer read
+            if (lane == 0) {
+                mbar_arrive(&empty[s]);
+                mbar_arrive(&abar[rg]);           // next block published; current block no longer read
+            }
         }
 
         // epilogue: W = sigma2 * acc + nugget * X[global row]
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
-            const int64_t lrow = tile * KC_BM + rg * 16 + h * 8 + g;
-            if (lrow < p.mloc) {
+            const int64_t lrow = (base_rg + rg) * 16 + h * 8 + g;
+            if (active && lrow < p.mloc) {
                 double* wrow = p.W + lrow * p.ldw + nb0 * 8 + 2 * t;
                 const double* xg = p.X + (p.row0 + lrow) * p.ld + nb0 * 8 + 2 * t;
 #pragma unroll
@@ -228,19 +333,19 @@ static void launch_kcov(gsi_ctx* ctx, const KcovParams& p0) {
     const int ld = NB * 8 + 4;
     const size_t stage_bytes = (size_t)(KC_BK * ld + 3 * KC_BK) * sizeof(double);
     const size_t a_bytes = (size_t)2 * KC_BM * KC_AP * sizeof(double);
-    int stages = (int)((224 * 1024 - a_bytes - 256) / stage_bytes);
+    int stages = (int)((224 * 1024 - a_bytes - 1024) / stage_bytes);
     if (stages > 4) stages = 4;
     if (stages < 2) stages = 2;
     p.stages = stages;
-    const size_t smem = stages * stage_bytes + a_bytes + 2 * stages * sizeof(uint64_t);
+    const size_t smem = stages * stage_bytes + a_bytes + (2 * stages + 4) * sizeof(uint64_t) + 64 * sizeof(double);
     auto kfn = kcov_gemm_kernel<NB, KIND, DIM>;
     GSI_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int occ = 0;
     GSI_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kfn, KC_THREADS, smem));
     if (occ < 1) occ = 1;
-    const int64_t ntiles = (p.mloc + KC_BM - 1) / KC_BM;
+    const int64_t total_rg = (p.mloc + 15) / 16;                 // 16-row groups; a CTA runs up to 4 at a time
     int64_t grid = (int64_t)ctx->num_sms * occ;
-    if (grid > ntiles) grid = ntiles;
+    if (grid > total_rg) grid = total_rg;
     if (grid < 1) grid = 1;
     kfn<<<(unsigned)grid, KC_THREADS, smem, ctx->stream>>>(p);
     GSI_CUDA(cudaGetLastError());
