@@ -95,11 +95,26 @@ __device__ __forceinline__ double fast_exp_neg(double y, const double* __restric
     return e < -1000 ? 0.0 : res;
 }
 
+// sqrt(x) for x > 0 (callers add 1e-300 so the diagonal r2 = 0 stays finite): hardware
+// rsqrt seed (MUFU, 2^-22) + two Goldschmidt steps = 6 FP64 pipe instructions, <= 2 ulp.
+__device__ __forceinline__ double fast_sqrt_pos(double x) {
+    double rs;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(rs) : "d"(x));
+    double h = __hiloint2double(__double2hiint(rs) - 0x00100000, __double2loint(rs));   // rs / 2
+    double g = x * rs;
+    double r = fma(-g, h, 0.5);
+    g = fma(g, r, g);
+    h = fma(h, r, h);
+    r = fma(-g, h, 0.5);
+    g = fma(g, r, g);
+    return g;
+}
+
 // kind-specific value from r2.  For the Gaussian kernel the coordinates handed to the
 // kernel are pre-scaled by 1/sqrt(2) so that r2 already carries the factor 1/2.
 template <int KIND>
 __device__ __forceinline__ double kern_eval(double r2, double beta, const double* __restrict__ tab) {
-    if (KIND == GSI_KERNEL_EXPONENTIAL) return fast_exp_neg(sqrt(r2), tab);
+    if (KIND == GSI_KERNEL_EXPONENTIAL) return fast_exp_neg(fast_sqrt_pos(r2), tab);
     if (KIND == GSI_KERNEL_GAUSSIAN) return fast_exp_neg(r2, tab);
     return exp(-beta * log1p(r2));
 }
@@ -202,11 +217,11 @@ __global__ void __launch_bounds__(KC_THREADS, 1) kcov_gemm_kernel(const __grid_c
     auto gen4 = [&](const double (&ui)[DIM], const double* u0, int64_t ustride, double (&v)[4]) {
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
-            double r2 = 0.0;
+            double r2 = (KIND == GSI_KERNEL_EXPONENTIAL) ? 1e-300 : 0.0;
 #pragma unroll
             for (int k = 0; k < DIM; ++k) {
                 const double dk = ui[k] - u0[k * ustride + gj0 + e];
-                r2 += dk * dk;
+                r2 = fma(dk, dk, r2);
             }
             v[e] = kern_eval<KIND>(r2, p.beta, etab);
         }
@@ -272,11 +287,11 @@ __global__ void __launch_bounds__(KC_THREADS, 1) kcov_gemm_kernel(const __grid_c
                 // is live at a time and its DFMAs interleave with this step's DMMAs
                 if ((ks & 1) == 0 && gen_next) {
                     const int e = ks >> 1;
-                    double r2 = 0.0;
+                    double r2 = (KIND == GSI_KERNEL_EXPONENTIAL) ? 1e-300 : 0.0;
 #pragma unroll
                     for (int k = 0; k < DIM; ++k) {
                         const double dk = ui[k] - us[k * KC_BK + gj0 + e];
-                        r2 += dk * dk;
+                        r2 = fma(dk, dk, r2);
                     }
                     anext[e] = kern_eval<KIND>(r2, p.beta, etab);
                 }
