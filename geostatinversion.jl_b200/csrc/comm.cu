@@ -91,6 +91,12 @@ void comm_allreduce_sum(gsi_ctx* ctx, double* buf, size_t count) {
                               ctx->stream));
 }
 
+void comm_broadcast(gsi_ctx* ctx, double* buf, size_t count, int root) {
+    if (ctx->world == 1) return;
+    GSI_NCCL(nccl().Broadcast(buf, buf, count, ncclDouble, root, reinterpret_cast<ncclComm_t>(ctx->nccl_comm),
+                              ctx->stream));
+}
+
 void comm_allgatherv(gsi_ctx* ctx, double* full, const int64_t* offsets, const int64_t* counts) {
     if (ctx->world == 1) return;
     ncclComm_t comm = reinterpret_cast<ncclComm_t>(ctx->nccl_comm);

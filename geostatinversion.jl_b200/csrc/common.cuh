@@ -127,6 +127,8 @@ void colmajor_download(const gsi_buf* b, double* host, int64_t ldh);
 void kcov_apply(gsi_op* op, const gsi_buf* X, gsi_buf* W);
 // ---- dense_gemm.cu : W = A X (trans=0) or A' X (trans=1); alpha scaling
 void dense_apply(gsi_ctx*, const gsi_buf* A, int trans, const gsi_buf* X, gsi_buf* W, double alpha);
+void tall_window_update(gsi_ctx*, const double* Pd, int64_t ldp, int64_t rows, int64_t kdim, const gsi_buf* X,
+                        double* Wd, int64_t ldw, double alpha);
 // ---- lu.cu : in place, returns unit-lower-trapezoidal L in LAPACK row order
 void lu_L_inplace(gsi_ctx*, gsi_buf* Y, int64_t row0_global, int64_t n_global, const int64_t* part_row0 /* world+1 */);
 // ---- qr.cu : in place thin Q; R (l x l, column-major, device) optional
@@ -137,6 +139,7 @@ void svd_small(gsi_ctx*, double* M, int l, double* U, double* sigma);
 // ---- comm.cu
 void comm_allgather(gsi_ctx*, const void* send, void* recv, size_t bytes_per_rank);
 void comm_allreduce_sum(gsi_ctx*, double* buf, size_t count);
+void comm_broadcast(gsi_ctx*, double* buf, size_t count, int root);
 // every rank r contributes counts[r] doubles placed at offsets[r] of `full` (in place ok)
 void comm_allgatherv(gsi_ctx*, double* full, const int64_t* offsets, const int64_t* counts);
 void comm_init(gsi_ctx*, const void* unique_id);

@@ -7,6 +7,13 @@
 // is the unit-lower-trapezoidal factor in LAPACK's *permuted* row order -- the reference
 // never un-permutes it.
 //
+// Blocked right-looking algorithm (panel width LU_PB): inside a panel only the panel's own
+// columns are eliminated column by column (the n x 16 panel stays L2-resident); after the
+// panel, U12 = L11^{-1} A12 is formed by one small kernel and the trailing matrix receives
+// ONE rank-LU_PB update on the FP64 tensor cores (tall_window_update -> dense DMMA GEMM),
+// i.e. it is read and written l/LU_PB times instead of l times.  Row interchanges always
+// move whole rows, as LAPACK's dlaswp does.
+//
 // One column = two launches on the context stream (no host sync):
 //   lu_pack      (1 CTA)  reduce the per-CTA pivot candidates of column k, export the
 //                         candidate row and (if owned) row k            -> send buffer
@@ -16,9 +23,11 @@
 //                         rank-1 update of the trailing columns, and -- fused -- the
 //                         arg-max search of column k+1.
 #include "common.cuh"
+#include "algos.h"
 
 namespace gsi {
 
+constexpr int LU_PB = 16;            // panel width
 constexpr int LU_THREADS = 256;
 constexpr int LU_WARPS = LU_THREADS / 32;
 
@@ -84,8 +93,10 @@ __global__ void lu_pack_kernel(const double* __restrict__ Y, int64_t ld, int64_t
         for (int j = threadIdx.x; j < l; j += LU_THREADS) send[2 + l + j] = Y[lk * ld + j];
 }
 
+// Elimination of column k restricted to the panel columns (k, jend).  8 rows per warp,
+// 4 lanes per row (a panel row segment is <= 15 contiguous doubles).
 __global__ void __launch_bounds__(LU_THREADS)
-lu_eliminate_kernel(double* __restrict__ Y, int64_t ld, int64_t nloc, int64_t row0, int l, int k,
+lu_eliminate_kernel(double* __restrict__ Y, int64_t ld, int64_t nloc, int64_t row0, int l, int k, int jend,
                     const double* __restrict__ recv, int world, int owner_k, Cand* __restrict__ cand,
                     int* __restrict__ flags) {
     extern __shared__ double sm[];
@@ -124,36 +135,44 @@ lu_eliminate_kernel(double* __restrict__ Y, int64_t ld, int64_t nloc, int64_t ro
     const bool use_recip = fabs(pivot) >= 2.2250738585072014e-308;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    // row k receives the pivot row (owner only, one CTA)
-    const int64_t lk = (int64_t)k - row0;
-    if (blockIdx.x == 0 && lk >= 0 && lk < nloc && p != k)
-        for (int j = threadIdx.x; j < l; j += LU_THREADS) Y[lk * ld + j] = prow[j];
+    if (blockIdx.x == 0 && p != k) {
+        // row k receives the pivot row (all columns); the part of old row k that this step does
+        // not rewrite (L part and columns beyond the panel) moves to position p
+        const int64_t lk = (int64_t)k - row0, lp = p - row0;
+        if (lk >= 0 && lk < nloc)
+            for (int j = threadIdx.x; j < l; j += LU_THREADS) Y[lk * ld + j] = prow[j];
+        if (lp >= 0 && lp < nloc)
+            for (int j = threadIdx.x; j < l; j += LU_THREADS)
+                if (j < k || j >= jend) Y[lp * ld + j] = krow[j];
+    }
 
+    const int sub = lane & 3, rsub = lane >> 2;
     double bv = -1.0, bi = 0.0;
     int64_t lstart = (int64_t)k + 1 - row0;
     if (lstart < 0) lstart = 0;
     const int64_t wglobal = (int64_t)blockIdx.x * LU_WARPS + warp;
     const int64_t wtotal = (int64_t)gridDim.x * LU_WARPS;
-    for (int64_t i = lstart + wglobal; i < nloc; i += wtotal) {
+    for (int64_t i = lstart + wglobal * 8 + rsub; i < nloc; i += wtotal * 8) {
         const int64_t gi = row0 + i;
         double* yrow = Y + i * ld;
-        const bool is_p = (gi == p);
-        const double* src = is_p ? krow : yrow;
+        const double* src = (gi == p) ? krow : yrow;
         double m;
         if (pivot == 0.0) m = src[k];
         else m = use_recip ? src[k] * rpiv : src[k] / pivot;
-        if (is_p) {
-            for (int j = lane; j < k; j += 32) yrow[j] = src[j];     // L part of the moved row
-        }
-        if (lane == 0) yrow[k] = m;
-        for (int j = k + 1 + lane; j < l; j += 32) {
+        if (sub == 0) yrow[k] = m;
+        for (int j = k + 1 + sub; j < jend; j += 4) {
             const double v = src[j] - m * prow[j];
             yrow[j] = v;
-            if (j == k + 1) {   // lane 0: candidate for the next column
+            if (j == k + 1) {   // sub == 0: candidate for the next column of this panel
                 const double a = fabs(v);
                 if (cand_better(a, (double)gi, bv, bi)) { bv = a; bi = (double)gi; }
             }
         }
+    }
+    // candidates live in lanes with sub == 0: reduce over the 8 row slots of the warp
+    for (int o = 4; o < 32; o <<= 1) {
+        const double ov = __shfl_xor_sync(0xffffffffu, bv, o), oi = __shfl_xor_sync(0xffffffffu, bi, o);
+        if (cand_better(ov, oi, bv, bi)) { bv = ov; bi = oi; }
     }
     if (lane == 0) { s_best[warp] = bv; s_bidx[warp] = bi; }
     __syncthreads();
@@ -161,6 +180,29 @@ lu_eliminate_kernel(double* __restrict__ Y, int64_t ld, int64_t nloc, int64_t ro
         for (int w = 1; w < LU_WARPS; ++w)
             if (cand_better(s_best[w], s_bidx[w], bv, bi)) { bv = s_best[w]; bi = s_bidx[w]; }
         cand[blockIdx.x].val = bv; cand[blockIdx.x].idx = bi;
+    }
+}
+
+// U12 = L11^{-1} A12 for the panel rows [ps, pe): one thread per trailing column.  The rows are
+// updated in place and copied to the small TALL buffer U (pb x (l - pe)) for the GEMM update.
+__global__ void lu_u12_kernel(double* __restrict__ Y, int64_t ld, int l, int ps, int pe, int64_t lrow_ps,
+                              double* __restrict__ U, int64_t ldu) {
+    const int j = pe + blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= l) return;
+    double u[LU_PB];
+    const int pb = pe - ps;
+#pragma unroll
+    for (int r = 0; r < LU_PB; ++r) {
+        if (r < pb) {
+            const double* yr = Y + (lrow_ps + r) * ld;
+            double v = yr[j];
+#pragma unroll
+            for (int c = 0; c < LU_PB; ++c)
+                if (c < r) v -= yr[ps + c] * u[c];
+            u[r] = v;
+            Y[(lrow_ps + r) * ld + j] = v;
+            U[(int64_t)r * ldu + (j - pe)] = v;
+        }
     }
 }
 
@@ -179,7 +221,7 @@ void lu_L_inplace(gsi_ctx* ctx, gsi_buf* Y, int64_t row0, int64_t n_global, cons
     GSI_REQUIRE(n_global >= l, GSI_ERR_UNSUPPORTED, "lu: fewer rows than columns is not supported");
     const int world = ctx->world;
     int grid = ctx->num_sms * 4;
-    const int64_t need = (nloc + LU_WARPS - 1) / LU_WARPS;
+    const int64_t need = (nloc + LU_WARPS * 8 - 1) / (LU_WARPS * 8);
     if (grid > need) grid = (int)(need > 0 ? need : 1);
     const size_t stride = 2 + 2 * (size_t)l;
     // scratch layout: cand[grid] | send[stride] | recv[world*stride]
@@ -189,24 +231,47 @@ void lu_L_inplace(gsi_ctx* ctx, gsi_buf* Y, int64_t row0, int64_t n_global, cons
     double* send = ctx->scratch + 2 * (size_t)grid;
     double* recv = (world > 1) ? send + stride : send;
     GSI_CUDA(cudaMemsetAsync(ctx->dflags, 0, sizeof(int), ctx->stream));
+    // the blocked path needs the first l rows (the pivot rows / U) on one rank
+    const int pb = (world > 1 && part_row0[1] < l) ? l : LU_PB;
+    const bool own_top = (world == 1) || (ctx->rank == 0);
 
-    lu_search_kernel<<<grid, LU_THREADS, 0, ctx->stream>>>(Y->d, Y->ld, nloc, row0, 0, cand);
-    GSI_CUDA(cudaGetLastError());
-    count_launch(ctx);
     const size_t smem = 2 * (size_t)l * sizeof(double);
-    for (int k = 0; k < l; ++k) {
-        lu_pack_kernel<<<1, LU_THREADS, 0, ctx->stream>>>(Y->d, Y->ld, nloc, row0, l, k, cand, grid, send);
+    for (int ps = 0; ps < l; ps += pb) {
+        const int pe = (ps + pb < l) ? ps + pb : l;
+        lu_search_kernel<<<grid, LU_THREADS, 0, ctx->stream>>>(Y->d, Y->ld, nloc, row0, ps, cand);
         GSI_CUDA(cudaGetLastError());
-        int owner_k = 0;
-        if (world > 1) {
-            comm_allgather(ctx, send, recv, stride * sizeof(double));
-            for (int r = 0; r < world; ++r)
-                if (k >= part_row0[r] && k < part_row0[r + 1]) owner_k = r;
+        count_launch(ctx);
+        for (int k = ps; k < pe; ++k) {
+            lu_pack_kernel<<<1, LU_THREADS, 0, ctx->stream>>>(Y->d, Y->ld, nloc, row0, l, k, cand, grid, send);
+            GSI_CUDA(cudaGetLastError());
+            int owner_k = 0;
+            if (world > 1) {
+                comm_allgather(ctx, send, recv, stride * sizeof(double));
+                for (int r = 0; r < world; ++r)
+                    if (k >= part_row0[r] && k < part_row0[r + 1]) owner_k = r;
+            }
+            lu_eliminate_kernel<<<grid, LU_THREADS, smem, ctx->stream>>>(Y->d, Y->ld, nloc, row0, l, k, pe, recv, world,
+                                                                          owner_k, cand, ctx->dflags);
+            GSI_CUDA(cudaGetLastError());
+            count_launch(ctx, 2);
         }
-        lu_eliminate_kernel<<<grid, LU_THREADS, smem, ctx->stream>>>(Y->d, Y->ld, nloc, row0, l, k, recv, world,
-                                                                      owner_k, cand, ctx->dflags);
-        GSI_CUDA(cudaGetLastError());
-        count_launch(ctx, 2);
+        if (pe < l) {
+            // U12 on the owner of the pivot rows, broadcast, then the rank-pb trailing update
+            BufPtr U = make_buf(ctx, GSI_LAYOUT_TALL, pe - ps, l - pe);
+            if (own_top) {
+                const int ncol = l - pe;
+                lu_u12_kernel<<<(ncol + 127) / 128, 128, 0, ctx->stream>>>(Y->d, Y->ld, l, ps, pe, (int64_t)ps - row0,
+                                                                           U->d, U->ld);
+                GSI_CUDA(cudaGetLastError());
+                count_launch(ctx);
+            }
+            if (world > 1) comm_broadcast(ctx, U->d, (size_t)U->rows_alloc * U->ld, 0);
+            int64_t i0 = (int64_t)pe - row0;
+            if (i0 < 0) i0 = 0;
+            if (i0 < nloc)
+                tall_window_update(ctx, Y->d + i0 * Y->ld + ps, Y->ld, nloc - i0, pe - ps, U.get(),
+                                   Y->d + i0 * Y->ld + pe, Y->ld, -1.0);
+        }
     }
     lu_finalize_kernel<<<l, 64, 0, ctx->stream>>>(Y->d, Y->ld, nloc, row0, l);
     GSI_CUDA(cudaGetLastError());
