@@ -232,6 +232,7 @@ def main():
         ctx.launch_count(reset=True)
         if with_timing:
             ctx.gemm_timing(enable=True)
+            ctx.phase_timing(reset=True)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(stream)
         for _ in range(steps):
@@ -241,6 +242,7 @@ def main():
         ms = e0.elapsed_time(e1)
         launches = ctx.launch_count()
         gemm = ctx.gemm_timing(enable=False) if with_timing else None
+        phases = ctx.phase_timing() if with_timing else None
         clocks = sampler.stop() if rank == 0 else None
         if dist is not None:
             tt = torch.tensor([ms], dtype=torch.float64, device="cuda")
@@ -249,11 +251,11 @@ def main():
             lt = torch.tensor([launches], dtype=torch.float64, device="cuda")
             dist.all_reduce(lt, op=dist.ReduceOp.SUM)
             launches = int(lt.item())
-        return ms, launches, gemm, clocks
+        return ms, launches, gemm, clocks, phases
 
     for _ in range(args.warmup):
         step_resident()
-    ms, launches, gemm, clocks = timed(step_resident, args.steps, True)
+    ms, launches, gemm, clocks, phases = timed(step_resident, args.steps, True)
     ms_per_step = ms / args.steps
     F = randsvd_flops(n, l, q)
     value = F / (ms_per_step * 1e-3) * 1e-12
@@ -261,7 +263,7 @@ def main():
     e2e = None
     if not args.no_e2e:
         step_e2e()
-        ms2, _, _, _ = timed(step_e2e, args.steps, False)
+        ms2, _, _, _, _ = timed(step_e2e, args.steps, False)
         e2e_ms = ms2 / args.steps
         e2e = {"value": F / (e2e_ms * 1e-3) * 1e-12, "unit": "TFLOP/s", "ms_per_step": e2e_ms,
                "h2d_bytes_per_step": int(world * n * l * 8), "d2h_bytes_per_step": int(n * l * 8)}
@@ -283,7 +285,8 @@ def main():
                "config": {"workload": desc, "n": n, "K": K, "p": p, "q": q, "kernel": kind, "ell": list(ell),
                           "normaliser": "LU_REF", "parallelism": f"row-shard x{world}",
                           "l2": "operand streams (X 366 MB/pass) exceed L2; no flush needed"},
-               "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roof}
+               "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roof,
+               "phase_ms_per_step": {k: v / args.steps for k, v in phases.items()}}
         if not args.no_cpu_baseline and world == 1:
             tf, cms, sample, cores = cpu_oracle_run(args.workload, 1, 1)
             out["cpu_baseline"] = {"value": tf, "unit": "TFLOP/s", "cores": cores, "kind": "port", "sample": sample,

@@ -69,6 +69,13 @@ class Context:
         check(self._lib.gsi_ctx_gemm_timing(self._h, flag, C.byref(ms), C.byref(n), C.byref(fl)))
         return ms.value, n.value, fl.value
 
+    def phase_timing(self, reset=False):
+        """ms per phase recorded while gemm timing is on: products, lu, qr, small svd, back-multiply."""
+        out = (C.c_double * 8)()
+        check(self._lib.gsi_ctx_phase_timing(self._h, out, 1 if reset else 0))
+        names = ["products", "lu", "qr", "svd_small", "backmul"]
+        return {n: out[i] for i, n in enumerate(names)}
+
     def close(self):
         if getattr(self, "_h", None) and self._h:
             self._lib.gsi_ctx_destroy(self._h)

@@ -36,7 +36,7 @@ void BufDeleter::operator()(gsi_buf* b) const {
 }
 
 // ------------------------------------------------------------------ operator application
-static void timed_begin(gsi_ctx* ctx) {
+void phase_begin(gsi_ctx* ctx) {
     if (!ctx->time_gemm) return;
     if (ctx->ev_used + 2 > ctx->ev_pool.size()) {
         for (int i = 0; i < 64; ++i) {
@@ -47,22 +47,31 @@ static void timed_begin(gsi_ctx* ctx) {
     }
     GSI_CUDA(cudaEventRecord(ctx->ev_pool[ctx->ev_used], ctx->stream));
 }
-static void timed_end(gsi_ctx* ctx, double flops, int nlaunch) {
+void phase_end(gsi_ctx* ctx, int phase) {
     if (!ctx->time_gemm) return;
     GSI_CUDA(cudaEventRecord(ctx->ev_pool[ctx->ev_used + 1], ctx->stream));
     ctx->ev_used += 2;
+    ctx->ev_phase.push_back(phase);
+}
+static void timed_begin(gsi_ctx* ctx) { phase_begin(ctx); }
+static void timed_end(gsi_ctx* ctx, double flops, int nlaunch) {
+    if (!ctx->time_gemm) return;
+    phase_end(ctx, PH_GEMM);
     ctx->gemm_launches += nlaunch;
     ctx->gemm_flops_accum += flops;
 }
-// resolve the recorded event pairs into gemm_ms_accum
+// resolve the recorded event pairs into gemm_ms_accum / phase_ms
 void resolve_gemm_timing(gsi_ctx* ctx) {
-    for (size_t i = 0; i + 1 < ctx->ev_used; i += 2) {
+    for (size_t i = 0, j = 0; i + 1 < ctx->ev_used; i += 2, ++j) {
         GSI_CUDA(cudaEventSynchronize(ctx->ev_pool[i + 1]));
         float ms = 0.f;
         GSI_CUDA(cudaEventElapsedTime(&ms, ctx->ev_pool[i], ctx->ev_pool[i + 1]));
-        ctx->gemm_ms_accum += ms;
+        const int ph = ctx->ev_phase[j];
+        ctx->phase_ms[ph] += ms;
+        if (ph == PH_GEMM) ctx->gemm_ms_accum += ms;
     }
     ctx->ev_used = 0;
+    ctx->ev_phase.clear();
 }
 
 // Y = op(A) X.   X: all rows of the operand on this rank.  Output distribution:
@@ -135,6 +144,8 @@ static bool op_symmetric(const gsi_op* op) { return op->type != OP_DENSE; }
 // In-place normalisation of a (possibly row-sharded) iterate.
 static void normalise_lu(gsi_op* op, gsi_buf* Y, bool sharded) {
     gsi_ctx* ctx = op->ctx;
+    phase_begin(ctx);
+    struct End { gsi_ctx* c; ~End() { phase_end(c, PH_LU); } } end_{ctx};
     if (sharded && ctx->world > 1) {
         lu_L_inplace(ctx, Y, op->row0, op->m, op->part.data());
     } else {
@@ -149,6 +160,8 @@ static void normalise_lu(gsi_op* op, gsi_buf* Y, bool sharded) {
 // local Q <- Q_local * Qtilde_block.  Rdev (l x l col-major, device) optional.
 void tsqr_thinQ(gsi_op* op, gsi_buf* Y, bool sharded, double* Rdev) {
     gsi_ctx* ctx = op->ctx;
+    phase_begin(ctx);
+    struct End { gsi_ctx* c; ~End() { phase_end(c, PH_QR); } } end_{ctx};
     const int l = (int)Y->cols;
     if (!(sharded && ctx->world > 1)) {
         qr_thinQ_inplace(ctx, Y, Rdev);
@@ -304,7 +317,9 @@ void randsvd(gsi_op* op, const gsi_buf* Omega, int64_t K, int64_t p, int64_t q, 
     double* Usc = small + (size_t)2 * l * l;
     double* sigma = small + (size_t)3 * l * l;
     tsqr_thinQ(op, Bt.buf.get(), Bt.sharded, R);
+    phase_begin(ctx);
     svd_small(ctx, R, l, U, sigma);
+    phase_end(ctx, PH_SVD);
     // Z = V * Diagonal(sqrt.([S[1:K]; zeros(p)]))                        (:87-88)
     scale_cols_kernel<<<(l * l + 255) / 256, 256, 0, ctx->stream>>>(U, sigma, l, (int)K, Usc);
     GSI_CUDA(cudaGetLastError());
@@ -314,7 +329,9 @@ void randsvd(gsi_op* op, const gsi_buf* Omega, int64_t K, int64_t p, int64_t q, 
     Iterate Z;
     Z.buf = make_buf(ctx, GSI_LAYOUT_TALL, Bt.buf->rows, l);
     Z.sharded = Bt.sharded;
+    phase_begin(ctx);
     tall_times_small(ctx, Bt.buf.get(), Mt.get(), Z.buf.get());
+    phase_end(ctx, PH_BACKMUL);
     if (S_host) {
         GSI_CUDA(cudaMemcpyAsync(S_host, sigma, (size_t)l * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
     }

@@ -173,6 +173,15 @@ GSI_API int32_t gsi_ctx_gemm_timing(gsi_ctx* ctx, int32_t enable, double* ms_out
     });
 }
 
+GSI_API int32_t gsi_ctx_phase_timing(gsi_ctx* ctx, double* ms_out8, int32_t reset) {
+    return guarded([&] {
+        use(ctx);
+        resolve_gemm_timing(ctx);
+        if (ms_out8) for (int i = 0; i < 8; ++i) ms_out8[i] = ctx->phase_ms[i];
+        if (reset) for (int i = 0; i < 8; ++i) ctx->phase_ms[i] = 0.0;
+    });
+}
+
 // ---- buffers
 GSI_API int32_t gsi_buf_alloc(gsi_ctx* ctx, int32_t layout, int64_t rows, int64_t cols, gsi_buf** out) {
     return guarded([&] {

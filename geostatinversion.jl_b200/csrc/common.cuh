@@ -71,6 +71,8 @@ struct gsi_ctx {
     // (synchronised + summed) only when the host queries them, so timing adds no sync
     std::vector<cudaEvent_t> ev_pool;
     size_t ev_used = 0;
+    std::vector<int> ev_phase;           // phase id of each recorded pair
+    double phase_ms[8] = {0, 0, 0, 0, 0, 0, 0, 0};   // 0 gemm, 1 lu, 2 qr, 3 small svd, 4 back-multiply
     // caching device allocator for iterate buffers: cudaMalloc/cudaFree of ~350 MB blocks
     // cost milliseconds and synchronise the device, so freed blocks are kept for reuse
     std::vector<std::pair<size_t, void*>> free_blocks;
@@ -147,6 +149,10 @@ void comm_destroy(gsi_ctx*);
 void comm_unique_id(void* out128);
 
 inline void count_launch(gsi_ctx* c, int n = 1) { c->launches += n; }
+// ---- algos.cu: event-pair phase timing (active only while time_gemm is on)
+enum Phase { PH_GEMM = 0, PH_LU = 1, PH_QR = 2, PH_SVD = 3, PH_BACKMUL = 4 };
+void phase_begin(gsi_ctx*);
+void phase_end(gsi_ctx*, int phase);
 // ---- api.cu: pooled device memory
 void* pool_alloc(gsi_ctx*, size_t bytes);
 void pool_free(gsi_ctx*, void* p, size_t bytes);

@@ -3,100 +3,92 @@
 // LAPACK dgeqp3 + dorgqr; only range(Q) matters) and the QR of B' that
 // precedes the small SVD (`svd(B)`, :86).
 //
-// Local factorisation: LAPACK dgeqr2/dlarfg reflectors, one column per step, each step =
-//   qr_house  (1 CTA)  reduce the dot products  g_j = sum_{i>k} Y[i,k] Y[i,j]  that the
-//                      previous update accumulated, form (beta, tau, 1/(alpha-beta)),
-//                      update row k, publish tau*w_j
-//   qr_update (grid)   one read+write pass over the trailing rows: scale column k to v,
-//                      apply the reflector, and -- fused -- accumulate the dot products
-//                      the NEXT column needs (warp-shuffle broadcast of the column-(k+1)
-//                      entry, per-lane partial sums, one block reduction at the end).
-// Q is then formed in place by the same two-kernel pattern run backwards (dorg2r).
-// Across GPUs the R factors are all-gathered and re-factored redundantly (TSQR).
+// Blocked (compact-WY) algorithm with panels of QB = 16 columns, LAPACK dgeqrt/dorgqr style:
+//   panel factorisation  column by column with dgeqr2/dlarfg reflectors, but touching only
+//                        the n x 16 panel (L2-resident): per column one single-CTA kernel
+//                        (Householder scalars from the dot products the previous pass
+//                        accumulated, row-k update) and one grid pass (scale column k to v,
+//                        apply the reflector to the panel, and -- fused -- accumulate the
+//                        next column's dot products: 4 lanes per row, warp-shuffle
+//                        broadcast/reduction);
+//   T factor             G = V'V by the DMMA Gram kernel + dlarft recurrence (16 x 16);
+//   trailing update      W = V'Y2 (DMMA Gram kernel, split over row chunks, deterministic
+//                        two-stage reduction), W <- T'W, Y2 -= V W on the dense DMMA GEMM
+//                        (tall_window_update): the trailing matrix is read/written l/16 times.
+// Q is formed by the same block reflectors applied backwards (dorgqr): Q2 -= V (T (V'Q2)),
+// panel columns Q1 = E - V (T V_top').  Across GPUs the R factors are all-gathered and
+// re-factored redundantly (TSQR, algos.cu).
 #include "common.cuh"
+#include "algos.h"
+#include "ptx.cuh"
+#include "nb_list.h"
 
 namespace gsi {
 
-constexpr int QR_THREADS = 1024;     // 32 warps/SM: the update pass is latency-bound with fewer
-constexpr int QR_WARPS = QR_THREADS / 32;
-constexpr int QR_MAXC = (kMaxCols + 31) / 32;   // column chunks of 32 per lane
+constexpr int QB = 16;               // panel width
+constexpr int QP_THREADS = 256;      // panel column-step kernels
+constexpr int QP_WARPS = QP_THREADS / 32;
+constexpr int GR_THREADS = 256;      // Gram kernel: 8 warps, each a private row chunk
+constexpr int GR_WARPS = GR_THREADS / 32;
 
-// partial[b][j] (b = CTA) -> reduced in the *_house kernels
 struct QrScal { double tau, scale, beta, pad; };
 
-__device__ __forceinline__ double block_reduce_sum(double v, double* sh) {
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    if (lane == 0) sh[warp] = v;
-    __syncthreads();
-    double r = 0.0;
-    if (threadIdx.x < QR_WARPS) r = sh[threadIdx.x];
-    if (warp == 0) {
-        for (int o = 16; o > 0; o >>= 1) r += __shfl_xor_sync(0xffffffffu, r, o);
-        if (lane == 0) sh[0] = r;
-    }
-    __syncthreads();
-    r = sh[0];
-    __syncthreads();
-    return r;
-}
-
-// Shared accumulation epilogue: psum[c] holds this lane's partial for column j0 + lane + 32c.
-__device__ __forceinline__ void store_partials(const double (&psum)[QR_MAXC], int j0, int l, double* sm /*[QR_WARPS][l]*/,
-                                               double* __restrict__ partial_row) {
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+// ----------------------------------------------------------------------------- panel steps
+// Accumulate, for rows i in (kdot, n):  part[jj] = sum_i Y[i, kdot] * Y[i, ps + jj]  (jj < pb).
+// Shared epilogue of the panel kernels: lanes hold psum[c] for panel column (sub + 4c).
+__device__ __forceinline__ void panel_store_partials(double (&psum)[4], double* __restrict__ part_cta) {
+    __shared__ double s_part[QP_WARPS][QB];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, sub = lane & 3;
 #pragma unroll
-    for (int c = 0; c < QR_MAXC; ++c) {
-        const int j = j0 + lane + 32 * c;
-        if (j < l) sm[warp * l + j] = psum[c];
+    for (int c = 0; c < 4; ++c) {
+        double v = psum[c];
+        for (int o = 4; o < 32; o <<= 1) v += __shfl_xor_sync(0xffffffffu, v, o);   // over the 8 row slots
+        if (lane < 4) s_part[warp][sub + 4 * c] = v;
     }
     __syncthreads();
-    for (int j = j0 + threadIdx.x; j < l; j += QR_THREADS) {
+    if (threadIdx.x < QB) {
         double s = 0.0;
 #pragma unroll
-        for (int w = 0; w < QR_WARPS; ++w) s += sm[w * l + j];
-        partial_row[j] = s;
+        for (int w = 0; w < QP_WARPS; ++w) s += s_part[w][threadIdx.x];
+        part_cta[threadIdx.x] = s;
     }
 }
 
-// g_j = sum_{i > 0} Y[i,0] * Y[i,j]  (initial dot products for column 0)
-__global__ void __launch_bounds__(QR_THREADS)
-qr_dots0_kernel(const double* __restrict__ Y, int64_t ld, int64_t n, int l, double* __restrict__ partial) {
-    extern __shared__ double sm[];
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    double psum[QR_MAXC];
-#pragma unroll
-    for (int c = 0; c < QR_MAXC; ++c) psum[c] = 0.0;
-    for (int64_t i = 1 + (int64_t)blockIdx.x * QR_WARPS + warp; i < n; i += (int64_t)gridDim.x * QR_WARPS) {
+// dots of the first panel column with the panel columns, rows > ps
+__global__ void __launch_bounds__(QP_THREADS)
+qr_panel_dots_kernel(const double* __restrict__ Y, int64_t ld, int64_t n, int ps, int pe, double* __restrict__ partial) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, sub = lane & 3, rsub = lane >> 2;
+    double psum[4] = {0.0, 0.0, 0.0, 0.0};
+    const int64_t wglobal = (int64_t)blockIdx.x * QP_WARPS + warp, wtotal = (int64_t)gridDim.x * QP_WARPS;
+    for (int64_t i = ps + 1 + wglobal * 8 + rsub; i < n; i += wtotal * 8) {
         const double* yrow = Y + i * ld;
-        const double y0 = yrow[0];
+        const double y0 = yrow[ps];
 #pragma unroll
-        for (int c = 0; c < QR_MAXC; ++c) {
-            const int j = lane + 32 * c;
-            if (j < l) psum[c] += y0 * yrow[j];
+        for (int c = 0; c < 4; ++c) {
+            const int j = ps + sub + 4 * c;
+            if (j < pe) psum[c] += y0 * yrow[j];
         }
     }
-    store_partials(psum, 0, l, sm, partial + (size_t)blockIdx.x * l);
+    panel_store_partials(psum, partial + (size_t)blockIdx.x * QB);
 }
 
-constexpr int QH_THREADS = 256;      // single-CTA scalar kernels
-// Householder scalars of column k + row-k update.  tw[j] = tau * w_j for j > k.
-__global__ void __launch_bounds__(QH_THREADS)
-qr_house_kernel(double* __restrict__ Y, int64_t ld, int l, int k, const double* __restrict__ partial, int nparts,
-                double* __restrict__ tw, double* __restrict__ taus, QrScal* __restrict__ scal) {
-    __shared__ double s_g[kMaxCols];
+// Householder scalars of column k (dlarfg) + row-k update inside the panel.  tw[jj] = tau*w_j.
+__global__ void __launch_bounds__(QP_THREADS)
+qr_house_kernel(double* __restrict__ Y, int64_t ld, int ps, int pe, int k, const double* __restrict__ partial,
+                int nparts, double* __restrict__ tw, double* __restrict__ taus, QrScal* __restrict__ scal) {
+    __shared__ double s_g[QB];
     __shared__ double s_tau, s_scale;
-    for (int j = k + threadIdx.x; j < l; j += QH_THREADS) {
+    if (threadIdx.x < QB) {
         double s = 0.0;
-        for (int b = 0; b < nparts; ++b) s += partial[(size_t)b * l + j];
-        s_g[j] = s;
+        for (int b = 0; b < nparts; ++b) s += partial[(size_t)b * QB + threadIdx.x];
+        s_g[threadIdx.x] = s;
     }
     __syncthreads();
     if (threadIdx.x == 0) {
         const double alpha = Y[(int64_t)k * ld + k];
-        const double xnorm2 = s_g[k];
+        const double xnorm2 = s_g[k - ps];
         double tau = 0.0, scale = 0.0, beta = alpha;
-        if (xnorm2 > 0.0) {                         // dlarfg
+        if (xnorm2 > 0.0) {
             const double nrm = sqrt(alpha * alpha + xnorm2);
             beta = (alpha >= 0.0) ? -nrm : nrm;
             tau = (beta - alpha) / beta;
@@ -109,112 +101,279 @@ qr_house_kernel(double* __restrict__ Y, int64_t ld, int l, int k, const double* 
     }
     __syncthreads();
     const double tau = s_tau, scale = s_scale;
-    for (int j = k + 1 + threadIdx.x; j < l; j += QH_THREADS) {
+    const int j = k + 1 + threadIdx.x;
+    if (j < pe) {
         const double ykj = Y[(int64_t)k * ld + j];
-        const double w = ykj + scale * s_g[j];      // v' * Y[:, j]   (v_k = 1)
+        const double w = ykj + scale * s_g[j - ps];         // v' * Y[:, j]   (v_k = 1)
         const double t = tau * w;
         Y[(int64_t)k * ld + j] = ykj - t;
-        tw[j] = t;
+        tw[j - ps] = t;
     }
 }
 
-// rows i > k: Y[i,k] <- v_i = scale*Y[i,k];  Y[i,j] -= v_i*tw[j];  accumulate next dots.
-__global__ void __launch_bounds__(QR_THREADS)
-qr_update_kernel(double* __restrict__ Y, int64_t ld, int64_t n, int l, int k, const double* __restrict__ tw,
+// rows i > k: Y[i,k] <- v_i = scale*Y[i,k]; Y[i,j] -= v_i*tw[j] for panel columns j > k;
+// fused: dot products of the new column k+1 with the panel columns (rows > k+1).
+__global__ void __launch_bounds__(QP_THREADS)
+qr_update_kernel(double* __restrict__ Y, int64_t ld, int64_t n, int ps, int pe, int k, const double* __restrict__ tw,
                  const QrScal* __restrict__ scal, double* __restrict__ partial) {
-    extern __shared__ double sm[];      // [QR_WARPS][l] + tw copy [l]
-    double* s_tw = sm + QR_WARPS * l;
-    for (int j = threadIdx.x; j < l; j += QR_THREADS) s_tw[j] = (j > k) ? tw[j] : 0.0;
+    __shared__ double s_tw[QB];
+    if (threadIdx.x < QB) s_tw[threadIdx.x] = (ps + (int)threadIdx.x > k && ps + (int)threadIdx.x < pe) ? tw[threadIdx.x] : 0.0;
     __syncthreads();
     const double scale = scal->scale;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    double psum[QR_MAXC];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, sub = lane & 3, rsub = lane >> 2;
+    double psum[4] = {0.0, 0.0, 0.0, 0.0};
+    const int64_t wglobal = (int64_t)blockIdx.x * QP_WARPS + warp, wtotal = (int64_t)gridDim.x * QP_WARPS;
+    const int niter_guard = (int)((n - (k + 1) + wtotal * 8 - 1) / (wtotal * 8));
+    for (int it = 0; it < niter_guard; ++it) {
+        const int64_t i = k + 1 + (wglobal + (int64_t)it * wtotal) * 8 + rsub;
+        const bool valid = i < n;
+        double nv[4] = {0.0, 0.0, 0.0, 0.0};
+        if (valid) {
+            double* yrow = Y + i * ld;
+            const double v = scale * yrow[k];
 #pragma unroll
-    for (int c = 0; c < QR_MAXC; ++c) psum[c] = 0.0;
-    const int nchunks = (l - k + 31) / 32;
-    for (int64_t i = k + 1 + (int64_t)blockIdx.x * QR_WARPS + warp; i < n; i += (int64_t)gridDim.x * QR_WARPS) {
-        double* yrow = Y + i * ld;
-        const double v = scale * yrow[k];
-        double nv[QR_MAXC];
-#pragma unroll
-        for (int c = 0; c < QR_MAXC; ++c) {
-            nv[c] = 0.0;
-            if (c < nchunks) {
-                const int j = k + lane + 32 * c;
-                if (j < l) {
-                    nv[c] = (j == k) ? v : yrow[j] - v * s_tw[j];
+            for (int c = 0; c < 4; ++c) {
+                const int j = ps + sub + 4 * c;
+                if (j >= k && j < pe) {
+                    nv[c] = (j == k) ? v : yrow[j] - v * s_tw[j - ps];
                     yrow[j] = nv[c];
                 }
             }
         }
-        // column k+1 entry lives in lane 1 of chunk 0
-        const double ynext = __shfl_sync(0xffffffffu, nv[0], 1);
-        if (i > k + 1) {
+        // the new column k+1 entry of this row: panel slot (k+1-ps) -> lane sub = slot & 3, chunk slot >> 2
+        const int slot = k + 1 - ps;
+        double mine = 0.0;
 #pragma unroll
-            for (int c = 0; c < QR_MAXC; ++c) psum[c] += ynext * nv[c];
+        for (int c = 0; c < 4; ++c)
+            if (c == (slot >> 2)) mine = nv[c];
+        const double ynext = __shfl_sync(0xffffffffu, mine, (lane & ~3) | (slot & 3));
+        if (valid && i > k + 1) {
+#pragma unroll
+            for (int c = 0; c < 4; ++c) psum[c] += ynext * nv[c];
         }
     }
-    store_partials(psum, k, l, sm, partial + (size_t)blockIdx.x * l);
+    panel_store_partials(psum, partial + (size_t)blockIdx.x * QB);
 }
 
-// ---- explicit Q (dorg2r), backwards ---------------------------------------------------------
-// Step k: d_j = sum_{i>k} v_k[i] Q[i,j] arrives in `partial` (rows i > k; accumulated by the
-// previous org_update, i.e. of step k+1).
-__global__ void __launch_bounds__(QH_THREADS)
-org_house_kernel(double* __restrict__ Y, int64_t ld, int l, int k, const double* __restrict__ partial, int nparts,
-                 const double* __restrict__ taus, double* __restrict__ tw) {
-    const double tau = taus[k];
-    for (int j = k + 1 + threadIdx.x; j < l; j += QH_THREADS) {
-        double d = 0.0;
-        for (int b = 0; b < nparts; ++b) d += partial[(size_t)b * l + j];
-        const double qkj = Y[(int64_t)k * ld + j];
-        const double w = qkj + d;
-        const double t = tau * w;
-        Y[(int64_t)k * ld + j] = qkj - t;
-        tw[j] = t;
-    }
-    // column k above the diagonal holds R entries: Q has zeros there
-    for (int i = threadIdx.x; i < k; i += QH_THREADS) Y[(int64_t)i * ld + k] = 0.0;
-    if (threadIdx.x == 0) Y[(int64_t)k * ld + k] = 1.0 - tau;
-}
-
-// rows i > k: Q[i,j] -= v_i*tw[j] (j > k), Q[i,k] = -tau*v_i; accumulate dots with v_{k-1}.
-__global__ void __launch_bounds__(QR_THREADS)
-org_update_kernel(double* __restrict__ Y, int64_t ld, int64_t n, int l, int k, const double* __restrict__ tw,
-                  const double* __restrict__ taus, double* __restrict__ partial) {
-    extern __shared__ double sm[];
-    double* s_tw = sm + QR_WARPS * l;
-    for (int j = threadIdx.x; j < l; j += QR_THREADS) s_tw[j] = (j > k) ? tw[j] : 0.0;
-    __syncthreads();
-    const double tau = taus[k];
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    double psum[QR_MAXC];
+// ----------------------------------------------------------------------------- Gram kernel
+// partial[cta][a][j] = sum over this CTA's rows of P1[i, a] * P2[i, j],  a < 16, j < 8*NB.
+// P1 / P2 are windows of TALL buffers (pointer + pitch); columns >= c1 / >= c2 read as zero.
+template <int NB>
+__global__ void __launch_bounds__(GR_THREADS)
+gram_kernel(const double* __restrict__ P1, int64_t ld1, int c1, const double* __restrict__ P2, int64_t ld2, int c2,
+            int64_t rows, double* __restrict__ partial) {
+    extern __shared__ double s_tile[];                  // [16][8*NB]
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane >> 2, t = lane & 3;
+    constexpr int lp = 8 * NB;
+    constexpr int NBW = (NB + 3) / 4;                   // n-blocks per warp (4 column groups)
+    for (int i = threadIdx.x; i < 16 * lp; i += GR_THREADS) s_tile[i] = 0.0;
+    // 8 warps = 2 row chunks x 4 column groups; a row chunk is contiguous, multiple of 4 rows
+    const int cg = warp & 3, rc = warp >> 2;
+    const int nb0 = cg * NBW;
+    const int64_t nchunks = (int64_t)gridDim.x * 2;
+    int64_t chunk = (rows + nchunks - 1) / nchunks;
+    chunk = (chunk + 3) / 4 * 4;
+    const int64_t r0 = ((int64_t)blockIdx.x * 2 + rc) * chunk;
+    int64_t r1 = r0 + chunk;
+    if (r1 > rows) r1 = rows;
+    double acc[2][NBW][2];
 #pragma unroll
-    for (int c = 0; c < QR_MAXC; ++c) psum[c] = 0.0;
-    const int nchunks = (l - k + 31) / 32;
-    for (int64_t i = k + 1 + (int64_t)blockIdx.x * QR_WARPS + warp; i < n; i += (int64_t)gridDim.x * QR_WARPS) {
-        double* yrow = Y + i * ld;
-        const double v = yrow[k];
-        const double vprev = (k > 0) ? yrow[k - 1] : 0.0;
+    for (int h = 0; h < 2; ++h)
 #pragma unroll
-        for (int c = 0; c < QR_MAXC; ++c) {
-            if (c < nchunks) {
-                const int j = k + lane + 32 * c;
-                if (j < l) {
-                    const double nv = (j == k) ? -tau * v : yrow[j] - v * s_tw[j];
-                    yrow[j] = nv;
-                    psum[c] += vprev * nv;
-                }
+        for (int nb = 0; nb < NBW; ++nb) { acc[h][nb][0] = 0.0; acc[h][nb][1] = 0.0; }
+    const bool a0ok = g < c1, a1ok = 8 + g < c1;
+    for (int64_t i0 = r0; i0 < r1; i0 += 4) {
+        const int64_t i = i0 + t;
+        const bool rok = i < r1;
+        const double a0 = (rok && a0ok) ? P1[i * ld1 + g] : 0.0;
+        const double a1 = (rok && a1ok) ? P1[i * ld1 + 8 + g] : 0.0;
+        const double* p2 = P2 + i * ld2 + nb0 * 8 + g;
+#pragma unroll
+        for (int nb = 0; nb < NBW; ++nb) {
+            if (nb0 + nb < NB) {
+                const double b = (rok && (nb0 + nb) * 8 + g < c2) ? p2[nb * 8] : 0.0;
+                dmma884(acc[0][nb][0], acc[0][nb][1], a0, b);
+                dmma884(acc[1][nb][0], acc[1][nb][1], a1, b);
             }
         }
     }
-    store_partials(psum, k, l, sm, partial + (size_t)blockIdx.x * l);
+    __syncthreads();
+    // deterministic accumulation: column groups are disjoint, the two row chunks add in order
+    for (int w = 0; w < 2; ++w) {
+        if (rc == w) {
+#pragma unroll
+            for (int h = 0; h < 2; ++h)
+#pragma unroll
+                for (int nb = 0; nb < NBW; ++nb) {
+                    if (nb0 + nb < NB) {
+                        s_tile[(h * 8 + g) * lp + (nb0 + nb) * 8 + 2 * t] += acc[h][nb][0];
+                        s_tile[(h * 8 + g) * lp + (nb0 + nb) * 8 + 2 * t + 1] += acc[h][nb][1];
+                    }
+                }
+        }
+        __syncthreads();
+    }
+    double* out = partial + (size_t)blockIdx.x * 16 * lp;
+    for (int i = threadIdx.x; i < 16 * lp; i += GR_THREADS) out[i] = s_tile[i];
 }
 
-// add row k's own term  v_{k-1}[k] * Q[k, j]  (j >= k) to partial slot 0 for step k-1
-__global__ void org_rowterm_kernel(const double* __restrict__ Y, int64_t ld, int l, int k, double* __restrict__ partial) {
-    const double vk = Y[(int64_t)k * ld + (k - 1)];
-    for (int j = k + threadIdx.x; j < l; j += blockDim.x) partial[j] += vk * Y[(int64_t)k * ld + j];
+template <int NB>
+static void launch_gram(gsi_ctx* ctx, int grid, const double* P1, int64_t ld1, int c1, const double* P2, int64_t ld2,
+                        int c2, int64_t rows, double* partial) {
+    const size_t smem = (size_t)16 * 8 * NB * sizeof(double);
+    gram_kernel<NB><<<grid, GR_THREADS, smem, ctx->stream>>>(P1, ld1, c1, P2, ld2, c2, rows, partial);
+    GSI_CUDA(cudaGetLastError());
+    count_launch(ctx);
+}
+
+// returns the number of partial tiles written (grid) and the tile pitch lp
+static void gram(gsi_ctx* ctx, const double* P1, int64_t ld1, int c1, const double* P2, int64_t ld2, int c2,
+                 int64_t rows, double* partial, int& nparts, int& lp) {
+    const int nb = nb_for_cols(c2);
+    GSI_REQUIRE(nb > 0, GSI_ERR_UNSUPPORTED, "gram: too many columns");
+    lp = 8 * nb;
+    int64_t grid = ctx->num_sms;
+    const int64_t need = (rows + 2 * 256 - 1) / (2 * 256);
+    if (grid > need) grid = need > 0 ? need : 1;
+    nparts = (int)grid;
+    switch (nb) {
+#define GSI_CASE(N) case N: launch_gram<N>(ctx, nparts, P1, ld1, c1, P2, ld2, c2, rows, partial); break;
+        GSI_NB_LIST(GSI_CASE)
+#undef GSI_CASE
+        default: throw Error(GSI_ERR_UNSUPPORTED, "gram: unsupported column-block count");
+    }
+}
+
+// ----------------------------------------------------------------------------- small block kernels
+// V_top[r][c] of the panel [ps, pe): unit lower triangular view of Y[ps+r, ps+c]
+__device__ __forceinline__ double vtop(const double* __restrict__ Y, int64_t ld, int ps, int r, int c) {
+    return r > c ? Y[(int64_t)(ps + r) * ld + ps + c] : (r == c ? 1.0 : 0.0);
+}
+
+// T factor of the panel (dlarft, forward columnwise): G = V'V from the Gram partials (rows >= pe)
+// plus the unit-lower top block.  T is pb x pb upper triangular, column-major with ld QB.
+__global__ void qr_tbuild_kernel(const double* __restrict__ Y, int64_t ld, int ps, int pe,
+                                 const double* __restrict__ gpart, int nparts, int glp,
+                                 const double* __restrict__ taus, double* __restrict__ T) {
+    __shared__ double G[QB][QB], Ts[QB][QB];
+    const int pb = pe - ps;
+    const int a = threadIdx.x / QB, c = threadIdx.x % QB;     // 256 threads
+    double s = 0.0;
+    if (a < pb && c < pb && a < c) {
+        for (int b = 0; b < nparts; ++b) s += gpart[(size_t)b * 16 * glp + a * glp + c];
+        for (int r = c; r < pb; ++r) s += vtop(Y, ld, ps, r, a) * vtop(Y, ld, ps, r, c);
+    }
+    G[a][c] = s;
+    Ts[a][c] = 0.0;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int cc = 0; cc < pb; ++cc) {
+            const double tau = taus[ps + cc];
+            // T[0:cc, cc] = -tau * T[0:cc, 0:cc] * G[0:cc, cc]
+            for (int r = 0; r < cc; ++r) {
+                double z = 0.0;
+                for (int m = r; m < cc; ++m) z += Ts[r][m] * G[m][cc];
+                Ts[r][cc] = -tau * z;
+            }
+            Ts[cc][cc] = tau;
+        }
+    }
+    __syncthreads();
+    T[c * QB + a] = Ts[a][c];
+}
+
+// One thread per trailing column j (window column jj): W = V'Y2 (Gram partials over rows >= pe
+// + top block), W2 = op(T) W  (transT = 1: T'W, factorisation; 0: T W, forming Q),
+// top rows Y2[ps+r, j] -= sum_c V_top[r][c] W2[c], and W2 -> TALL buffer for the GEMM update.
+__global__ void qr_wt_kernel(double* __restrict__ Y, int64_t ld, int ps, int pe, int j0, int ncols,
+                             const double* __restrict__ wpart, int nparts, int wlp, const double* __restrict__ T,
+                             int transT, double* __restrict__ W2, int64_t ldw2) {
+    __shared__ double Ts[QB][QB], Vt[QB][QB];
+    const int pb = pe - ps;
+    for (int i = threadIdx.x; i < QB * QB; i += blockDim.x) {
+        const int r = i / QB, c = i % QB;
+        Ts[r][c] = (r < pb && c < pb) ? T[c * QB + r] : 0.0;
+        Vt[r][c] = (r < pb && c < pb) ? vtop(Y, ld, ps, r, c) : 0.0;
+    }
+    __syncthreads();
+    const int jj = blockIdx.x * blockDim.x + threadIdx.x;
+    if (jj >= ncols) return;
+    const int j = j0 + jj;
+    double w[QB], y2[QB];
+#pragma unroll
+    for (int r = 0; r < QB; ++r) y2[r] = (r < pb) ? Y[(int64_t)(ps + r) * ld + j] : 0.0;
+#pragma unroll
+    for (int c = 0; c < QB; ++c) {
+        double s = 0.0;
+        if (c < pb) {
+            for (int b = 0; b < nparts; ++b) s += wpart[(size_t)b * 16 * wlp + c * wlp + jj];
+#pragma unroll
+            for (int r = 0; r < QB; ++r) s += Vt[r][c] * y2[r];
+        }
+        w[c] = s;
+    }
+    double w2[QB];
+#pragma unroll
+    for (int c = 0; c < QB; ++c) {
+        double s = 0.0;
+#pragma unroll
+        for (int m = 0; m < QB; ++m) s += (transT ? Ts[m][c] : Ts[c][m]) * w[m];
+        w2[c] = s;
+    }
+#pragma unroll
+    for (int r = 0; r < QB; ++r) {
+        if (r < pb) {
+            double s = y2[r];
+#pragma unroll
+            for (int c = 0; c < QB; ++c) s -= Vt[r][c] * w2[c];
+            Y[(int64_t)(ps + r) * ld + j] = s;
+            W2[(int64_t)r * ldw2 + jj] = w2[r];
+        }
+    }
+}
+
+// M = T * V_top' (pb x pb, row-major [a][c]) for the panel columns of Q
+__global__ void org_m_kernel(const double* __restrict__ Y, int64_t ld, int ps, int pe, const double* __restrict__ T,
+                             double* __restrict__ Mout) {
+    const int pb = pe - ps;
+    const int a = threadIdx.x / QB, c = threadIdx.x % QB;
+    double s = 0.0;
+    if (a < pb && c < pb)
+        for (int m = a; m < pb; ++m) s += T[m * QB + a] * vtop(Y, ld, ps, c, m);       // T[a][m] * V_top[c][m]
+    Mout[a * QB + c] = s;
+}
+
+// Panel columns of Q: Q[:, ps:pe] = E - V M.  One thread per row i >= ps (each thread reads and
+// rewrites only its own row).
+__global__ void org_panel_kernel(double* __restrict__ Y, int64_t ld, int64_t n, int ps, int pe,
+                                 const double* __restrict__ Min) {
+    __shared__ double M[QB][QB];
+    const int pb = pe - ps;
+    if (threadIdx.x < QB * QB) M[threadIdx.x / QB][threadIdx.x % QB] = Min[threadIdx.x];
+    __syncthreads();
+    const int64_t i = ps + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double* yrow = Y + i * ld + ps;
+    double v[QB];
+    const int r = (int)(i - ps);
+#pragma unroll
+    for (int a = 0; a < QB; ++a) {
+        double x = 0.0;
+        if (a < pb) {
+            if (i >= pe) x = yrow[a];
+            else x = (r > a) ? yrow[a] : (r == a ? 1.0 : 0.0);
+        }
+        v[a] = x;
+    }
+#pragma unroll
+    for (int c = 0; c < QB; ++c) {
+        if (c < pb) {
+            double s = (i < pe && r == c) ? 1.0 : 0.0;
+#pragma unroll
+            for (int a = 0; a < QB; ++a) s -= v[a] * M[a][c];
+            yrow[c] = s;
+        }
+    }
 }
 
 __global__ void extract_R_kernel(const double* __restrict__ Y, int64_t ld, int l, double* __restrict__ R) {
@@ -224,50 +383,103 @@ __global__ void extract_R_kernel(const double* __restrict__ Y, int64_t ld, int l
     R[(size_t)c * l + r] = (r <= c) ? Y[(int64_t)r * ld + c] : 0.0;
 }
 
+// the R entries (on and above the diagonal) are not part of Q
+__global__ void zero_upper_kernel(double* __restrict__ Y, int64_t ld, int l) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= l * l) return;
+    const int r = idx % l, c = idx / l;
+    if (r <= c) Y[(int64_t)r * ld + c] = 0.0;
+}
+
 void qr_thinQ_inplace(gsi_ctx* ctx, gsi_buf* Y, double* Rdev) {
     GSI_REQUIRE(Y->layout == GSI_LAYOUT_TALL, GSI_ERR_INVALID_ARGUMENT, "qr: TALL buffer required");
     const int l = (int)Y->cols;
     const int64_t n = Y->rows;
     GSI_REQUIRE(n >= l, GSI_ERR_UNSUPPORTED, "qr: fewer (local) rows than columns is not supported");
-    int grid = ctx->num_sms;
-    const int64_t need = (n + QR_WARPS - 1) / QR_WARPS;
-    if (grid > need) grid = (int)(need > 0 ? need : 1);
-    // scratch: partial[grid*l] | tw[l] | taus[l] | scal
-    const size_t need_doubles = (size_t)grid * l + 2 * (size_t)l + 8;
-    GSI_REQUIRE(need_doubles <= ctx->scratch_doubles, GSI_ERR_UNSUPPORTED, "qr: scratch too small");
-    double* partial = ctx->scratch;
-    double* tw = partial + (size_t)grid * l;
-    double* taus = tw + l;
-    QrScal* scal = reinterpret_cast<QrScal*>(taus + l);
-    const size_t smem_upd = ((size_t)QR_WARPS * l + l) * sizeof(double);
-    const size_t smem_dot = (size_t)QR_WARPS * l * sizeof(double);
     cudaStream_t st = ctx->stream;
-    GSI_CUDA(cudaFuncSetAttribute(qr_update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_upd));
-    GSI_CUDA(cudaFuncSetAttribute(org_update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_upd));
-    GSI_CUDA(cudaFuncSetAttribute(qr_dots0_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_dot));
+    int grid = ctx->num_sms * 2;
+    const int64_t need = (n + QP_WARPS * 8 - 1) / (QP_WARPS * 8);
+    if (grid > need) grid = (int)(need > 0 ? need : 1);
+    const int npanels = (l + QB - 1) / QB;
+    const int lpmax = 8 * nb_for_cols(l);
+    // scratch: partial[grid*QB] | tw[QB] | scal | taus[l] | T[npanels*QB*QB] | gpart[num_sms*16*lpmax]
+    double* partial = ctx->scratch;
+    double* tw = partial + (size_t)grid * QB;
+    QrScal* scal = reinterpret_cast<QrScal*>(tw + QB);
+    double* taus = tw + QB + 4;
+    double* Tall = taus + l;
+    double* Mscr = Tall + (size_t)npanels * QB * QB;
+    double* gpart = Mscr + QB * QB;
+    const size_t need_doubles = (size_t)(gpart - ctx->scratch) + (size_t)ctx->num_sms * 16 * lpmax;
+    GSI_REQUIRE(need_doubles <= ctx->scratch_doubles, GSI_ERR_UNSUPPORTED, "qr: scratch too small");
 
-    qr_dots0_kernel<<<grid, QR_THREADS, smem_dot, st>>>(Y->d, Y->ld, n, l, partial);
-    GSI_CUDA(cudaGetLastError());
-    count_launch(ctx);
-    for (int k = 0; k < l; ++k) {
-        qr_house_kernel<<<1, QH_THREADS, 0, st>>>(Y->d, Y->ld, l, k, partial, grid, tw, taus, scal);
-        qr_update_kernel<<<grid, QR_THREADS, smem_upd, st>>>(Y->d, Y->ld, n, l, k, tw, scal, partial);
+    // ---------------- factorisation, panel by panel
+    for (int ps = 0, pi = 0; ps < l; ps += QB, ++pi) {
+        const int pe = (ps + QB < l) ? ps + QB : l;
+        double* T = Tall + (size_t)pi * QB * QB;
+        qr_panel_dots_kernel<<<grid, QP_THREADS, 0, st>>>(Y->d, Y->ld, n, ps, pe, partial);
+        for (int k = ps; k < pe; ++k) {
+            qr_house_kernel<<<1, QP_THREADS, 0, st>>>(Y->d, Y->ld, ps, pe, k, partial, grid, tw, taus, scal);
+            qr_update_kernel<<<grid, QP_THREADS, 0, st>>>(Y->d, Y->ld, n, ps, pe, k, tw, scal, partial);
+        }
         GSI_CUDA(cudaGetLastError());
-        count_launch(ctx, 2);
+        count_launch(ctx, 1 + 2 * (pe - ps));
+        // T factor: G = V'V (rows >= pe through the Gram kernel, top block inside qr_tbuild)
+        int nparts = 0, glp = 0;
+        const int64_t rows_below = n - pe;
+        gram(ctx, Y->d + (int64_t)pe * Y->ld + ps, Y->ld, pe - ps, Y->d + (int64_t)pe * Y->ld + ps, Y->ld, pe - ps,
+             rows_below, gpart, nparts, glp);
+        qr_tbuild_kernel<<<1, QB * QB, 0, st>>>(Y->d, Y->ld, ps, pe, gpart, nparts, glp, taus, T);
+        GSI_CUDA(cudaGetLastError());
+        count_launch(ctx);
+        if (pe < l) {
+            // trailing update: Y2 <- (I - V T' V') Y2
+            const int ncols = l - pe;
+            int wparts = 0, wlp = 0;
+            gram(ctx, Y->d + (int64_t)pe * Y->ld + ps, Y->ld, pe - ps, Y->d + (int64_t)pe * Y->ld + pe, Y->ld, ncols,
+                 rows_below, gpart, wparts, wlp);
+            BufPtr W2 = make_buf(ctx, GSI_LAYOUT_TALL, pe - ps, ncols);
+            qr_wt_kernel<<<(ncols + 63) / 64, 64, 0, st>>>(Y->d, Y->ld, ps, pe, pe, ncols, gpart, wparts, wlp, T, 1,
+                                                           W2->d, W2->ld);
+            GSI_CUDA(cudaGetLastError());
+            count_launch(ctx);
+            tall_window_update(ctx, Y->d + (int64_t)pe * Y->ld + ps, Y->ld, rows_below, pe - ps, W2.get(),
+                               Y->d + (int64_t)pe * Y->ld + pe, Y->ld, -1.0);
+        }
     }
     if (Rdev) {
         extract_R_kernel<<<(l * l + 255) / 256, 256, 0, st>>>(Y->d, Y->ld, l, Rdev);
         GSI_CUDA(cudaGetLastError());
         count_launch(ctx);
     }
-    // ---- form Q in place, k = l-1 .. 0
-    GSI_CUDA(cudaMemsetAsync(partial, 0, (size_t)grid * l * sizeof(double), st));
-    for (int k = l - 1; k >= 0; --k) {
-        org_house_kernel<<<1, QH_THREADS, 0, st>>>(Y->d, Y->ld, l, k, partial, grid, taus, tw);
-        org_update_kernel<<<grid, QR_THREADS, smem_upd, st>>>(Y->d, Y->ld, n, l, k, tw, taus, partial);
-        if (k > 0) org_rowterm_kernel<<<1, QH_THREADS, 0, st>>>(Y->d, Y->ld, l, k, partial);
+    // ---------------- explicit Q, panels backwards (dorgqr)
+    zero_upper_kernel<<<(l * l + 255) / 256, 256, 0, st>>>(Y->d, Y->ld, l);
+    GSI_CUDA(cudaGetLastError());
+    count_launch(ctx);
+    for (int pi = npanels - 1; pi >= 0; --pi) {
+        const int ps = pi * QB;
+        const int pe = (ps + QB < l) ? ps + QB : l;
+        const double* T = Tall + (size_t)pi * QB * QB;
+        const int64_t rows_below = n - pe;
+        if (pe < l) {
+            const int ncols = l - pe;
+            int wparts = 0, wlp = 0;
+            gram(ctx, Y->d + (int64_t)pe * Y->ld + ps, Y->ld, pe - ps, Y->d + (int64_t)pe * Y->ld + pe, Y->ld, ncols,
+                 rows_below, gpart, wparts, wlp);
+            BufPtr W2 = make_buf(ctx, GSI_LAYOUT_TALL, pe - ps, ncols);
+            qr_wt_kernel<<<(ncols + 63) / 64, 64, 0, st>>>(Y->d, Y->ld, ps, pe, pe, ncols, gpart, wparts, wlp, T, 0,
+                                                           W2->d, W2->ld);
+            GSI_CUDA(cudaGetLastError());
+            count_launch(ctx);
+            tall_window_update(ctx, Y->d + (int64_t)pe * Y->ld + ps, Y->ld, rows_below, pe - ps, W2.get(),
+                               Y->d + (int64_t)pe * Y->ld + pe, Y->ld, -1.0);
+        }
+        const int64_t prow = n - ps;
+        org_m_kernel<<<1, QB * QB, 0, st>>>(Y->d, Y->ld, ps, pe, T, Mscr);
+        org_panel_kernel<<<(unsigned)((prow + 255) / 256), 256, 0, st>>>(Y->d, Y->ld, n, ps, pe, Mscr);
+        count_launch(ctx);
         GSI_CUDA(cudaGetLastError());
-        count_launch(ctx, k > 0 ? 3 : 2);
+        count_launch(ctx);
     }
 }
 

@@ -96,6 +96,10 @@ int32_t gsi_ctx_launch_count(gsi_ctx* ctx, int64_t* count_out, int32_t reset);
 int32_t gsi_ctx_gemm_timing(gsi_ctx* ctx, int32_t enable, double* ms_out, int64_t* launches_out,
                             double* flops_out);
 
+/* CUDA-event time per phase while gemm timing is enabled: ms_out8[0] operator products,
+ * [1] LU normaliser, [2] QR/TSQR, [3] small SVD, [4] back-multiplication; [5..7] reserved. */
+int32_t gsi_ctx_phase_timing(gsi_ctx* ctx, double* ms_out8, int32_t reset);
+
 /* ---- device buffers (replace Julia `Matrix{Float64}` temporaries) ----------------- */
 int32_t gsi_buf_alloc(gsi_ctx* ctx, int32_t layout, int64_t rows, int64_t cols, gsi_buf** out);
 int32_t gsi_buf_free(gsi_buf* buf); /* idempotent on NULL, never throws (Julia finalizer) */
