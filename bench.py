@@ -150,6 +150,8 @@ def main():
     ap.add_argument("--impl", default="gsi", choices=["gsi", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--generation", default="table", choices=["table", "arithmetic"],
+                    help="kernel values: lattice-table look-up (structured grid) or exp/sqrt arithmetic from coordinates")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -197,7 +199,10 @@ def main():
     coords = grid_coords(grid)
     n = coords.shape[1]
     row0, mloc = gsi.partition_rows(n, world, rank)
-    op = gsi.KernelCovMatrix(kind, coords, ell, ctx=ctx, row0=row0, mloc=mloc)
+    if args.generation == "table":
+        op = gsi.GridKernelCovMatrix(kind, grid, ell, ctx=ctx, row0=row0, mloc=mloc)
+    else:
+        op = gsi.KernelCovMatrix(kind, coords, ell, ctx=ctx, row0=row0, mloc=mloc)
 
     # host-seeded Omega in pinned memory (the reference draws randn(n, l) on the host)
     omega_pinned = torch.empty((l, n), dtype=torch.float64, pin_memory=True)      # (l, n) C-order == (n, l) F-order
@@ -284,6 +289,8 @@ def main():
                "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
                "config": {"workload": desc, "n": n, "K": K, "p": p, "q": q, "kernel": kind, "ell": list(ell),
                           "normaliser": "LU_REF", "parallelism": f"row-shard x{world}",
+                          "kernel_values": ("lattice table look-up (structured grid, n distinct values)"
+                                            if args.generation == "table" else "exp/sqrt arithmetic from coordinates"),
                           "l2": "operand streams (X 366 MB/pass) exceed L2; no flush needed"},
                "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roof,
                "phase_ms_per_step": {k: v / args.steps for k, v in phases.items()}}

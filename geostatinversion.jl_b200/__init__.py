@@ -9,7 +9,7 @@ from . import _lib
 from ._lib import (GsiError, SingularException, PosDefException, DimensionMismatch, NoDeviceError,
                    LAYOUT_TALL, LAYOUT_COLMAJOR, KERNEL_EXPONENTIAL, KERNEL_GAUSSIAN, KERNEL_POWERLAW,
                    NORMALISER_LU_REF, NORMALISER_QR)
-from .core import (Context, DeviceMatrix, DenseMatrix, LowRankCovMatrix, KernelCovMatrix, default_context,
+from .core import (Context, DeviceMatrix, DenseMatrix, LowRankCovMatrix, KernelCovMatrix, GridKernelCovMatrix, default_context,
                    set_default_context, as_operator, partition_rows)
 from . import randmatfact as RandMatFact
 from .randmatfact import randsvd, rangefinder, eig_nystrom

@@ -319,6 +319,29 @@ class KernelCovMatrix(_Operator):
                                          float(nugget), float(beta), self.row0, self.mloc, C.byref(self._h)))
 
 
+class GridKernelCovMatrix(_Operator):
+    """KernelCovMatrix for points on a structured grid (shape[0] fastest = Julia linear index of
+    an array of size `shape`; coordinates idx .* spacing).  A stationary kernel on a lattice has
+    only prod(shape) distinct values, which are tabulated once; the product kernel looks them up
+    by lattice offset instead of evaluating exp/sqrt on the FP64 pipe it shares with the tensor
+    MMAs.  Identical products to KernelCovMatrix(kind, grid_coords(shape) * spacing, ell)."""
+    symmetric = True
+
+    def __init__(self, kind, shape, ell, spacing=None, sigma2=1.0, nugget=0.0, beta=1.0, ctx=None, row0=0, mloc=None):
+        super().__init__(ctx or default_context())
+        shape = [int(s) for s in shape]
+        d = len(shape)
+        n = int(np.prod(shape))
+        dims = (C.c_int64 * d)(*shape)
+        spacing = np.ascontiguousarray(np.broadcast_to(np.asarray(1.0 if spacing is None else spacing, dtype=np.float64), (d,)))
+        ell = np.ascontiguousarray(np.broadcast_to(np.asarray(ell, dtype=np.float64), (d,)))
+        self.row0 = int(row0)
+        self.mloc = int(n - row0 if mloc is None else mloc)
+        self.kind = _KINDS[kind]
+        check(self._lib.gsi_op_kernelcov_grid(self.ctx._h, self.kind, d, dims, _pd(spacing), _pd(ell), float(sigma2),
+                                              float(nugget), float(beta), self.row0, self.mloc, C.byref(self._h)))
+
+
 def as_operator(A, ctx=None):
     if isinstance(A, _Operator):
         return A

@@ -4,6 +4,7 @@
 #include "common.cuh"
 #include "algos.h"
 #include <mutex>
+#include <cmath>
 
 #define GSI_API extern "C" __attribute__((visibility("default")))
 
@@ -356,11 +357,70 @@ GSI_API int32_t gsi_op_kernelcov(gsi_ctx* ctx, int32_t kind, int32_t d, int64_t 
     });
 }
 
+GSI_API int32_t gsi_op_kernelcov_grid(gsi_ctx* ctx, int32_t kind, int32_t d, const int64_t* dims, const double* spacing,
+                                      const double* ell, double sigma2, double nugget, double beta, int64_t row0,
+                                      int64_t mloc, gsi_op** out) {
+    return guarded([&] {
+        use(ctx);
+        GSI_REQUIRE(dims && spacing && ell && out, GSI_ERR_INVALID_ARGUMENT, "null argument");
+        GSI_REQUIRE(d >= 1 && d <= 3, GSI_ERR_UNSUPPORTED, "kernelcov_grid: d must be 1, 2 or 3");
+        GSI_REQUIRE(kind >= 0 && kind <= 2, GSI_ERR_INVALID_ARGUMENT, "kernelcov_grid: unknown kernel kind");
+        int64_t nd[3] = {1, 1, 1};
+        double h[3] = {1, 1, 1}, el[3] = {1, 1, 1};
+        int64_t n = 1;
+        for (int k = 0; k < d; ++k) {
+            GSI_REQUIRE(dims[k] >= 1 && ell[k] > 0.0, GSI_ERR_INVALID_ARGUMENT, "kernelcov_grid: bad dims / length scales");
+            nd[k] = dims[k]; h[k] = spacing[k]; el[k] = ell[k];
+            n *= dims[k];
+        }
+        GSI_REQUIRE(n < ((int64_t)1 << 31), GSI_ERR_UNSUPPORTED, "kernelcov_grid: more than 2^31 points");
+        GSI_REQUIRE(row0 >= 0 && mloc >= 0 && row0 + mloc <= n, GSI_ERR_INVALID_ARGUMENT, "kernelcov_grid: bad row block");
+        std::unique_ptr<gsi_op> op(new gsi_op());
+        op->ctx = ctx; op->type = OP_KERNELCOV; op->kind = kind; op->dim = d;
+        op->m = op->n = n; op->row0 = row0; op->mloc = mloc;
+        op->sigma2 = sigma2; op->nugget = nugget; op->beta = beta;
+        op->n_pad = round_up(n, kRowPad);
+        op->grid_nx = (int)nd[0]; op->grid_ny = (int)nd[1]; op->grid_nz = (int)nd[2];
+        // kernel value of every lattice offset (libm, same formula as the dense definition)
+        std::vector<double> tab((size_t)n);
+        for (int64_t dz = 0; dz < nd[2]; ++dz)
+            for (int64_t dy = 0; dy < nd[1]; ++dy)
+                for (int64_t dx = 0; dx < nd[0]; ++dx) {
+                    const double ux = (dx * h[0]) / el[0], uy = (dy * h[1]) / el[1], uz = (dz * h[2]) / el[2];
+                    double r2 = ux * ux;
+                    if (d > 1) r2 += uy * uy;
+                    if (d > 2) r2 += uz * uz;
+                    double v;
+                    if (kind == GSI_KERNEL_EXPONENTIAL) v = std::exp(-std::sqrt(r2));
+                    else if (kind == GSI_KERNEL_GAUSSIAN) v = std::exp(-0.5 * r2);
+                    else v = std::exp(-beta * std::log1p(r2));
+                    tab[(size_t)(dx + nd[0] * (dy + nd[1] * dz))] = v;
+                }
+        // lattice indices of every point (SoA, padding repeats the last point)
+        std::vector<int> lat((size_t)3 * op->n_pad, 0);
+        for (int64_t j = 0; j < op->n_pad; ++j) {
+            const int64_t jj = j < n ? j : n - 1;
+            lat[(size_t)0 * op->n_pad + j] = (int)(jj % nd[0]);
+            lat[(size_t)1 * op->n_pad + j] = (int)((jj / nd[0]) % nd[1]);
+            lat[(size_t)2 * op->n_pad + j] = (int)(jj / (nd[0] * nd[1]));
+        }
+        GSI_CUDA(cudaMalloc(&op->table, tab.size() * sizeof(double)));
+        GSI_CUDA(cudaMalloc(&op->lattice, lat.size() * sizeof(int)));
+        GSI_CUDA(cudaMemcpyAsync(op->table, tab.data(), tab.size() * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+        GSI_CUDA(cudaMemcpyAsync(op->lattice, lat.data(), lat.size() * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+        GSI_CUDA(cudaStreamSynchronize(ctx->stream));
+        set_partition(op.get());
+        *out = op.release();
+    });
+}
+
 GSI_API int32_t gsi_op_free(gsi_op* op) {
     if (!op) return GSI_OK;
     return guarded([&] {
         cudaSetDevice(op->ctx->device);
         if (op->ucoords) cudaFree(op->ucoords);
+        if (op->table) cudaFree(op->table);
+        if (op->lattice) cudaFree(op->lattice);
         if (op->tmpT) BufDeleter()(op->tmpT);
         delete op;
     });

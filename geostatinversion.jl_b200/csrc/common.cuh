@@ -108,6 +108,9 @@ struct gsi_op {
     double sigma2 = 1.0, nugget = 0.0, beta = 1.0;
     double* ucoords = nullptr;           // [dim][n_pad] scaled coordinates (SoA)
     int64_t n_pad = 0;
+    int* lattice = nullptr;              // structured grid: [3][n_pad] lattice indices
+    double* table = nullptr;             // structured grid: kernel value per lattice offset
+    int grid_nx = 1, grid_ny = 1, grid_nz = 1;
     std::vector<int64_t> part;           // row partition over ranks: part[r] .. part[r+1]
 };
 

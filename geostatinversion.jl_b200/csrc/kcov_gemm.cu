@@ -32,11 +32,15 @@ constexpr int KC_AP = KC_BK + 4;   // pitch of the generated A tile (4 mod 16 do
 constexpr int KC_WARPS = 16;
 constexpr int KC_THREADS = KC_WARPS * 32;
 constexpr int KC_CG = 4;           // column groups (warps sharing one row group)
+constexpr int KC_KIND_TABLE = 3;   // internal kind: stationary kernel on a structured grid, values from a lattice table
 
 struct KcovParams {
     const double* X;       // TALL, all n rows (zero padded), pitch ld
     double* W;             // TALL, local rows, pitch ldw
-    const double* u;       // scaled coordinates [3][n_pad]
+    const double* u;       // scaled coordinates [3][n_pad]              (arithmetic generation)
+    const int* lat;        // lattice indices [3][n_pad]                 (structured grid: table lookup)
+    const double* table;   // k(r2) for every lattice offset: table[dx + nx*(dy + ny*dz)]
+    int nx, ny;
     int64_t n;             // columns of C (= rows of X)
     int64_t n_pad;
     int64_t row0;          // first global row of this rank's block
@@ -116,6 +120,7 @@ template <int KIND>
 __device__ __forceinline__ double kern_eval(double r2, double beta, const double* __restrict__ tab) {
     if (KIND == GSI_KERNEL_EXPONENTIAL) return fast_exp_neg(fast_sqrt_pos(r2), tab);
     if (KIND == GSI_KERNEL_GAUSSIAN) return fast_exp_neg(r2, tab);
+    if (KIND == KC_KIND_TABLE) return 0.0;
     return exp(-beta * log1p(r2));
 }
 
@@ -179,7 +184,8 @@ __global__ void __launch_bounds__(KC_THREADS, 1) kcov_gemm_kernel(const __grid_c
         return full_rounds * per_round + b0;
     };
     const int64_t nkt = (p.n + KC_BK - 1) / KC_BK;
-    constexpr uint32_t stage_bytes = (uint32_t)((KC_BK * ld + DIM * KC_BK) * sizeof(double));
+    constexpr uint32_t stage_bytes = (uint32_t)(KC_BK * ld * sizeof(double) +
+                                                DIM * KC_BK * (KIND == KC_KIND_TABLE ? sizeof(int) : sizeof(double)));
 
     // ---------------- producer (thread 0): streams X / coordinate tiles ----------------------
     const int64_t total_it = my_rounds * nkt;
@@ -193,10 +199,15 @@ __global__ void __launch_bounds__(KC_THREADS, 1) kcov_gemm_kernel(const __grid_c
         double* us = xs + KC_BK * ld;
         mbar_expect_tx(&full[s], stage_bytes);
         bulk_g2s(xs, p.X + kt * KC_BK * p.ld, KC_BK * ld * 8, &full[s]);
-#pragma unroll
         const int64_t ktn = (kt + 1 == nkt) ? 0 : kt + 1;      // coordinates of the NEXT k-tile ride along
-        for (int k = 0; k < DIM; ++k)
-            bulk_g2s(us + k * KC_BK, p.u + k * p.n_pad + ktn * KC_BK, KC_BK * 8, &full[s]);
+        if (KIND == KC_KIND_TABLE) {
+            int* usi = reinterpret_cast<int*>(us);
+            for (int k = 0; k < DIM; ++k)
+                bulk_g2s(usi + k * KC_BK, p.lat + k * p.n_pad + ktn * KC_BK, KC_BK * 4, &full[s]);
+        } else {
+            for (int k = 0; k < DIM; ++k)
+                bulk_g2s(us + k * KC_BK, p.u + k * p.n_pad + ktn * KC_BK, KC_BK * 8, &full[s]);
+        }
     };
     if (tid == 0) {
         for (int64_t i = 0; i < lookahead && i < total_it; ++i) produce(i);
@@ -208,11 +219,26 @@ __global__ void __launch_bounds__(KC_THREADS, 1) kcov_gemm_kernel(const __grid_c
     const int gtid = tid & 127;                  // thread index within the row group
     const int grow_in_tile = rg * 16 + (gtid >> 3);
     const int gj0 = (gtid & 7) * 4;
+    int li[DIM];
     auto row_coords = [&](int64_t base_rg, double (&ui)[DIM]) {
         int64_t gpt = p.row0 + base_rg * 16 + grow_in_tile;           // global point of my generated row
         if (gpt > p.n - 1) gpt = p.n - 1;                             // tail rows: clamp (never stored)
 #pragma unroll
-        for (int k = 0; k < DIM; ++k) ui[k] = p.u[k * p.n_pad + gpt];
+        for (int k = 0; k < DIM; ++k) {
+            if (KIND == KC_KIND_TABLE) li[k] = p.lat[k * p.n_pad + gpt];
+            else ui[k] = p.u[k * p.n_pad + gpt];
+        }
+    };
+    // table variant: lattice offset of (my row, column point e of the tile) -> table index
+    auto table_index = [&](const int* usi, int e) -> int {
+        int idx = 0;
+#pragma unroll
+        for (int k = DIM - 1; k >= 0; --k) {
+            int dk = li[k] - usi[k * KC_BK + gj0 + e];
+            dk = dk < 0 ? -dk : dk;
+            idx = (k == DIM - 1) ? dk : idx * (k == 0 ? p.nx : p.ny) + dk;
+        }
+        return idx;
     };
     auto gen4 = [&](const double (&ui)[DIM], const double* u0, int64_t ustride, double (&v)[4]) {
 #pragma unroll
@@ -242,7 +268,21 @@ __global__ void __launch_bounds__(KC_THREADS, 1) kcov_gemm_kernel(const __grid_c
         row_coords(base_rg, ui);
         if (rg < nact) {
             double v[4];
-            gen4(ui, p.u, p.n_pad, v);
+            if (KIND == KC_KIND_TABLE) {
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    int idx = 0;
+#pragma unroll
+                    for (int k = DIM - 1; k >= 0; --k) {
+                        int dk = li[k] - p.lat[k * p.n_pad + gj0 + e];
+                        dk = dk < 0 ? -dk : dk;
+                        idx = (k == DIM - 1) ? dk : idx * (k == 0 ? p.nx : p.ny) + dk;
+                    }
+                    v[e] = __ldg(p.table + idx);
+                }
+            } else {
+                gen4(ui, p.u, p.n_pad, v);
+            }
             store4(a_tiles, v);
         }
         __syncwarp();
@@ -275,6 +315,14 @@ __global__ void __launch_bounds__(KC_THREADS, 1) kcov_gemm_kernel(const __grid_c
             if (last_kt) row_coords(base_next, ui);
             const bool gen_next = last_kt ? (rg < nact_next) : active;
             double* anext = a_tiles + (size_t)((it + 1) & 1) * a_doubles + grow_in_tile * KC_AP + gj0;
+            double tv[4] = {0.0, 0.0, 0.0, 0.0};
+            if (KIND == KC_KIND_TABLE && gen_next) {
+                // structured grid: the four kernel values are table look-ups (L1/L2 hits, no FP64 pipe
+                // work); issued now, consumed after the MMA loop
+                const int* usi = reinterpret_cast<const int*>(us);
+#pragma unroll
+                for (int e = 0; e < 4; ++e) tv[e] = __ldg(p.table + table_index(usi, e));
+            }
             // ---- tensor-core phase on the current k-tile: wait until the whole row group has
             //      published this block (and has stopped reading the other buffer)
             mbar_wait(&abar[rg], (uint32_t)(it & 1));
@@ -285,7 +333,7 @@ __global__ void __launch_bounds__(KC_THREADS, 1) kcov_gemm_kernel(const __grid_c
             for (int ks = 0; ks < KC_BK / 4; ++ks) {
                 // one kernel value of the NEXT k-tile every second k-step: a single exp chain
                 // is live at a time and its DFMAs interleave with this step's DMMAs
-                if ((ks & 1) == 0 && gen_next) {
+                if (KIND != KC_KIND_TABLE && (ks & 1) == 0 && gen_next) {
                     const int e = ks >> 1;
                     double r2 = (KIND == GSI_KERNEL_EXPONENTIAL) ? 1e-300 : 0.0;
 #pragma unroll
@@ -308,6 +356,11 @@ __global__ void __launch_bounds__(KC_THREADS, 1) kcov_gemm_kernel(const __grid_c
                         }
                     }
                 }
+            }
+            if (KIND == KC_KIND_TABLE && gen_next) {
+                double2* dst = reinterpret_cast<double2*>(anext);
+                dst[0] = make_double2(tv[0], tv[1]);
+                dst[1] = make_double2(tv[2], tv[3]);
             }
             __syncwarp();
             if (lane == 0) {
@@ -379,6 +432,7 @@ static void dispatch_kind(gsi_ctx* ctx, const KcovParams& p, int kind, int dim) 
         case GSI_KERNEL_EXPONENTIAL: dispatch_dim<NB, GSI_KERNEL_EXPONENTIAL>(ctx, p, dim); break;
         case GSI_KERNEL_GAUSSIAN: dispatch_dim<NB, GSI_KERNEL_GAUSSIAN>(ctx, p, dim); break;
         case GSI_KERNEL_POWERLAW: dispatch_dim<NB, GSI_KERNEL_POWERLAW>(ctx, p, dim); break;
+        case KC_KIND_TABLE: dispatch_dim<NB, KC_KIND_TABLE>(ctx, p, dim); break;
         default: throw Error(GSI_ERR_INVALID_ARGUMENT, "unknown covariance kernel kind");
     }
 }
@@ -395,12 +449,13 @@ void kcov_apply(gsi_op* op, const gsi_buf* X, gsi_buf* W) {
     GSI_REQUIRE(X->ld == 8 * nb + 4 && W->ld == X->ld, GSI_ERR_INVALID_ARGUMENT, "kernelcov apply: bad pitch");
     KcovParams p;
     p.X = X->d; p.W = W->d; p.u = op->ucoords;
+    p.lat = op->lattice; p.table = op->table; p.nx = op->grid_nx; p.ny = op->grid_ny;
     p.n = op->n; p.n_pad = op->n_pad; p.row0 = op->row0; p.mloc = op->mloc;
     p.ld = X->ld; p.ldw = W->ld;
     p.sigma2 = op->sigma2; p.nugget = op->nugget; p.beta = op->beta;
     p.stages = 0;
     switch (nb) {
-#define GSI_CASE(N) case N: dispatch_kind<N>(ctx, p, op->kind, op->dim); break;
+#define GSI_CASE(N) case N: dispatch_kind<N>(ctx, p, op->table ? KC_KIND_TABLE : op->kind, op->dim); break;
         GSI_NB_LIST(GSI_CASE)
 #undef GSI_CASE
         default: throw Error(GSI_ERR_UNSUPPORTED, "kernelcov apply: unsupported column-block count");

@@ -130,6 +130,15 @@ int32_t gsi_op_lowrankcov(gsi_ctx* ctx, gsi_buf* samples, int32_t remove_mean, g
 int32_t gsi_op_kernelcov(gsi_ctx* ctx, int32_t kind, int32_t d, int64_t n, const double* coords,
                          const double* ell, double sigma2, double nugget, double beta,
                          int64_t row0, int64_t mloc, gsi_op** out);
+/* The same operator for points on a STRUCTURED GRID (dims[0] fastest, Julia linear index;
+ * point coordinates idx .* spacing).  A stationary kernel on a lattice takes only
+ * prod(dims) distinct values (one per lattice offset), so they are tabulated once (libm on
+ * the host, O(n) memory) and the product kernel fetches C(x_i, x_j) by lattice offset --
+ * the n x n matrix is still never materialised and the FP64 pipe is left to the tensor
+ * MMAs.  Same products and parity contract as gsi_op_kernelcov.                        */
+int32_t gsi_op_kernelcov_grid(gsi_ctx* ctx, int32_t kind, int32_t d, const int64_t* dims,
+                              const double* spacing, const double* ell, double sigma2, double nugget,
+                              double beta, int64_t row0, int64_t mloc, gsi_op** out);
 int32_t gsi_op_free(gsi_op* op);
 /* size(A) (src/RandMatFact.jl:52-53, src/lowrank.jl:50-60)                           */
 int32_t gsi_op_size(const gsi_op* op, int64_t* m, int64_t* n);

@@ -31,6 +31,8 @@ def main():
         r0, ml = gsi.partition_rows(n, ctx.world, ctx.rank)
         op = gsi.KernelCovMatrix(kind, coords, ell, ctx=ctx, row0=r0, mloc=ml)
         Omega = np.random.default_rng(0).standard_normal((n, K + p))
+        if name == "gauss3d":       # structured-grid (lattice table) operator, sharded
+            op = gsi.GridKernelCovMatrix(kind, grid, ell, ctx=ctx, row0=r0, mloc=ml)
         Zfull = gsi.randsvd(op, K, p, q, Omega=Omega, full=True)
         Zloc = gsi.randsvd(op, K, p, q, Omega=Omega)
         assert Zloc.shape == (ml, K + p)

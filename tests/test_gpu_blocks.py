@@ -64,6 +64,27 @@ def test_kernelcov_apply(gsi, kind, grid, l):
     assert relerr(X[:, :3].T @ op, X[:, :3].T @ C) < 1e-12
 
 
+@pytest.mark.parametrize("kind", ["exponential", "gaussian", "powerlaw"])
+@pytest.mark.parametrize("grid,spacing,l", [((40, 30), (1.0, 1.0), 60), ((14, 12, 10), (1.0, 0.5, 2.0), 210),
+                                            ((1000,), (0.25,), 8), ((33, 31), (2.0, 3.0), 5), ((5, 1, 7), (1.0, 1.0, 1.0), 3)])
+def test_grid_kernelcov_apply(gsi, kind, grid, spacing, l):
+    """Structured-grid operator (lattice table look-up) vs the dense oracle and vs the
+    arithmetic-generation operator on the same points."""
+    rng = np.random.default_rng(len(grid) * 100 + l)
+    coords = oracle.grid_coords(grid, spacing)
+    d, n = coords.shape
+    ell = [3.1, 2.7, 2.3][:d]
+    kid = {"exponential": 0, "gaussian": 1, "powerlaw": 2}[kind]
+    C = oracle.kernel_cov_dense(kid, coords, ell, sigma2=1.7, nugget=0.01, beta=0.8)
+    X = rng.standard_normal((n, l))
+    op = gsi.GridKernelCovMatrix(kind, grid, ell, spacing=spacing, sigma2=1.7, nugget=0.01, beta=0.8)
+    assert op.shape == (n, n) and op.T is op
+    Y = op @ X
+    assert relerr(Y, C @ X) < 1e-12
+    Yc = gsi.KernelCovMatrix(kind, coords, ell, sigma2=1.7, nugget=0.01, beta=0.8) @ X
+    assert relerr(Y, Yc) < 1e-12
+
+
 def test_kernelcov_unstructured_points(gsi):
     rng = np.random.default_rng(5)
     n = 1234

@@ -92,6 +92,24 @@ def test_kernelcov_randsvd_parity(gsi, kind, grid, ell, K):
     assert np.max(np.abs(S[:K] - oracle.singvals_from_Z(Zref, K)) / S[:K]) < SV_TOL
 
 
+@pytest.mark.parametrize("kind,grid,ell,K", [
+    ("gaussian", (28, 26, 24), (9.0, 7.0, 5.0), 200),
+    ("exponential", (90, 80), (12.0, 8.0), 200),
+])
+def test_grid_kernelcov_randsvd_parity(gsi, kind, grid, ell, K):
+    """Same parity contract through the structured-grid (lattice table) operator."""
+    p, q = 10, 2
+    coords = oracle.grid_coords(grid)
+    n = coords.shape[1]
+    kid = {"exponential": 0, "gaussian": 1}[kind]
+    C = oracle.kernel_cov_dense(kid, coords, ell)
+    Omega = np.random.default_rng(0).standard_normal((n, K + p))
+    Zref = oracle.randsvd(C, Omega, K, p, q)
+    Z = gsi.randsvd(gsi.GridKernelCovMatrix(kind, grid, ell), K, p, q, Omega=Omega)
+    c = oracle.compare_Z(Z, Zref, K)
+    assert c["tail_zero"] and c["sv_rel"] < SV_TOL and c["sine"] < SINE_TOL, c
+
+
 def test_qr_normaliser_is_not_reference(gsi):
     """Documented behaviour: NORMALISER_QR is the textbook iteration, different from the
     reference's when rank(A) > K+p (F1) -- but still a valid range finder."""
