@@ -184,6 +184,11 @@ __global__ void __launch_bounds__(KC_THREADS, 1) kcov_gemm_kernel(const __grid_c
         return full_rounds * per_round + b0;
     };
     const int64_t nkt = (p.n + KC_BK - 1) / KC_BK;
+    // De-synchronised k sweeps: all CTAs in lockstep would request the SAME 56 KB X tile from the
+    // same few L2 slices at the same time.  CTA b starts its (cyclic) sweep kt0 tiles into X:
+    // 16 phase groups spread over a quarter of the sweep, so the set of tiles in flight stays
+    // L2-resident (<= 1/4 of X) while any one tile is wanted by ~148/16 SMs at a time.
+    const int64_t kt0 = ((int64_t)(blockIdx.x & 63) * nkt) / 256;
     constexpr uint32_t stage_bytes = (uint32_t)(KC_BK * ld * sizeof(double) +
                                                 DIM * KC_BK * (KIND == KC_KIND_TABLE ? sizeof(int) : sizeof(double)));
 
@@ -193,7 +198,8 @@ __global__ void __launch_bounds__(KC_THREADS, 1) kcov_gemm_kernel(const __grid_c
     auto produce = [&](int64_t nxt) {
         const int s = (int)(nxt % nstages);
         const uint32_t ph = (uint32_t)((nxt / nstages) & 1);
-        const int64_t kt = nxt % nkt;
+        int64_t kt = nxt % nkt + kt0;
+        if (kt >= nkt) kt -= nkt;
         mbar_wait(&empty[s], ph ^ 1u);
         double* xs = smem + (size_t)s * stage_doubles;
         double* us = xs + KC_BK * ld;
@@ -274,14 +280,14 @@ __global__ void __launch_bounds__(KC_THREADS, 1) kcov_gemm_kernel(const __grid_c
                     int idx = 0;
 #pragma unroll
                     for (int k = DIM - 1; k >= 0; --k) {
-                        int dk = li[k] - p.lat[k * p.n_pad + gj0 + e];
+                        int dk = li[k] - p.lat[k * p.n_pad + kt0 * KC_BK + gj0 + e];
                         dk = dk < 0 ? -dk : dk;
                         idx = (k == DIM - 1) ? dk : idx * (k == 0 ? p.nx : p.ny) + dk;
                     }
                     v[e] = __ldg(p.table + idx);
                 }
             } else {
-                gen4(ui, p.u, p.n_pad, v);
+                gen4(ui, p.u + kt0 * KC_BK, p.n_pad, v);
             }
             store4(a_tiles, v);
         }
