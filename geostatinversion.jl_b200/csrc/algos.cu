@@ -172,7 +172,15 @@ void tsqr_thinQ(gsi_op* op, gsi_buf* Y, bool sharded, double* Rdev) {
     GSI_CUDA(cudaMalloc(&Rall, (size_t)(G + 1) * l * l * sizeof(double)));
     std::unique_ptr<double, void (*)(double*)> guard(Rall, [](double* p) { cudaFree(p); });
     double* Rmine = Rall + (size_t)G * l * l;
-    qr_thinQ_inplace(ctx, Y, Rmine);
+    // a rank that owns fewer than l rows factors its block padded with zero rows (same R)
+    BufPtr padded;
+    gsi_buf* Yl = Y;
+    if (Y->rows < l) {
+        padded = make_buf(ctx, GSI_LAYOUT_TALL, l, l);
+        GSI_CUDA(cudaMemcpyAsync(padded->d, Y->d, (size_t)Y->rows * Y->ld * 8, cudaMemcpyDeviceToDevice, ctx->stream));
+        Yl = padded.get();
+    }
+    qr_thinQ_inplace(ctx, Yl, Rmine);
     comm_allgather(ctx, Rmine, Rall, (size_t)l * l * sizeof(double));
     // stack (G*l x l) as a TALL buffer
     BufPtr stack = make_buf(ctx, GSI_LAYOUT_TALL, (int64_t)G * l, l);
@@ -187,9 +195,9 @@ void tsqr_thinQ(gsi_op* op, gsi_buf* Y, bool sharded, double* Rdev) {
     BufPtr qt = make_buf(ctx, GSI_LAYOUT_TALL, l, l);
     GSI_CUDA(cudaMemcpyAsync(qt->d, stack->d + (size_t)ctx->rank * l * stack->ld, (size_t)l * stack->ld * 8,
                              cudaMemcpyDeviceToDevice, ctx->stream));
-    BufPtr tmp = make_buf(ctx, GSI_LAYOUT_TALL, Y->rows, l);
-    tall_times_small(ctx, Y, qt.get(), tmp.get());
-    tall_copy(ctx, tmp.get(), Y);
+    BufPtr tmp = make_buf(ctx, GSI_LAYOUT_TALL, Yl->rows, l);
+    tall_times_small(ctx, Yl, qt.get(), tmp.get());
+    GSI_CUDA(cudaMemcpyAsync(Y->d, tmp->d, (size_t)Y->rows * Y->ld * 8, cudaMemcpyDeviceToDevice, ctx->stream));
     GSI_CUDA(cudaStreamSynchronize(ctx->stream));
 }
 
