@@ -66,9 +66,7 @@ dense_gemm_kernel(const __grid_constant__ CUtensorMap amap, const __grid_constan
     const int64_t my_tiles = (ntiles > blockIdx.x) ? (ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
     const int64_t total_it = my_tiles * nkt;
     const int lookahead = nstages > 2 ? nstages - 2 : 1;
-    // cyclic k sweep with a per-CTA phase so that the CTAs do not all fetch the same X tile from
-    // the same L2 slices at the same time (see kcov_gemm.cu)
-    const int64_t kt0 = ((int64_t)(blockIdx.x & 63) * nkt) / 256;
+    const int64_t kt0 = 0;      // lock-step k sweeps keep the X stream L2-resident (see kcov_gemm.cu)
     auto produce = [&](int64_t nxt) {
         const int s = (int)(nxt % nstages);
         const uint32_t ph = (uint32_t)((nxt / nstages) & 1);

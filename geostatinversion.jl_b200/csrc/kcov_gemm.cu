@@ -41,6 +41,7 @@ struct KcovParams {
     const int* lat;        // lattice indices [3][n_pad]                 (structured grid: table lookup)
     const double* table;   // k(r2) for every lattice offset: table[dx + nx*(dy + ny*dz)]
     int nx, ny;
+    int sweep_groups, sweep_div, l2_hint;   // k-sweep de-synchronisation (power-of-two groups, spread = groups/div of X)
     int64_t n;             // columns of C (= rows of X)
     int64_t n_pad;
     int64_t row0;          // first global row of this rank's block
@@ -184,11 +185,14 @@ __global__ void __launch_bounds__(KC_THREADS, 1) kcov_gemm_kernel(const __grid_c
         return full_rounds * per_round + b0;
     };
     const int64_t nkt = (p.n + KC_BK - 1) / KC_BK;
-    // De-synchronised k sweeps: all CTAs in lockstep would request the SAME 56 KB X tile from the
-    // same few L2 slices at the same time.  CTA b starts its (cyclic) sweep kt0 tiles into X:
-    // 16 phase groups spread over a quarter of the sweep, so the set of tiles in flight stays
-    // L2-resident (<= 1/4 of X) while any one tile is wanted by ~148/16 SMs at a time.
-    const int64_t kt0 = ((int64_t)(blockIdx.x & 63) * nkt) / 256;
+    // Optional de-synchronised (cyclic) k sweeps, GSI_SWEEP="groups,div,hint": CTA b starts its sweep
+    // (b mod groups) * nkt/div tiles into X.  Measured on C3 (profiles/r01): 64 groups over a quarter
+    // of X gives +2.5 % (31.8 vs 31.0 TF/s) but the L2 hit rate of the X stream falls from 98 % to
+    // 26 % and the launch re-reads ~700 GB from HBM instead of 8.6 GB; small separations that keep
+    // the stream L2-resident give no gain.  Default: lock-step sweeps (groups = 1).
+    const int64_t kt_sep = nkt >= p.sweep_div ? nkt / p.sweep_div : (nkt >= 16 ? 1 : 0);
+    const int64_t kt0 = (int64_t)(blockIdx.x & (p.sweep_groups - 1)) * kt_sep;
+    const uint64_t xpolicy = l2_policy_evict_last();
     constexpr uint32_t stage_bytes = (uint32_t)(KC_BK * ld * sizeof(double) +
                                                 DIM * KC_BK * (KIND == KC_KIND_TABLE ? sizeof(int) : sizeof(double)));
 
@@ -204,7 +208,8 @@ __global__ void __launch_bounds__(KC_THREADS, 1) kcov_gemm_kernel(const __grid_c
         double* xs = smem + (size_t)s * stage_doubles;
         double* us = xs + KC_BK * ld;
         mbar_expect_tx(&full[s], stage_bytes);
-        bulk_g2s(xs, p.X + kt * KC_BK * p.ld, KC_BK * ld * 8, &full[s]);
+        if (p.l2_hint) bulk_g2s_hint(xs, p.X + kt * KC_BK * p.ld, KC_BK * ld * 8, &full[s], xpolicy);
+        else bulk_g2s(xs, p.X + kt * KC_BK * p.ld, KC_BK * ld * 8, &full[s]);
         const int64_t ktn = (kt + 1 == nkt) ? 0 : kt + 1;      // coordinates of the NEXT k-tile ride along
         if (KIND == KC_KIND_TABLE) {
             int* usi = reinterpret_cast<int*>(us);
@@ -456,6 +461,15 @@ void kcov_apply(gsi_op* op, const gsi_buf* X, gsi_buf* W) {
     KcovParams p;
     p.X = X->d; p.W = W->d; p.u = op->ucoords;
     p.lat = op->lattice; p.table = op->table; p.nx = op->grid_nx; p.ny = op->grid_ny;
+    {
+        static int groups = -1, div = -1, hint = -1;
+        if (groups < 0) {
+            const char* e = getenv("GSI_SWEEP");     // "groups,div,hint" (tuning knob; defaults below)
+            groups = 1; div = 256; hint = 0;
+            if (e) sscanf(e, "%d,%d,%d", &groups, &div, &hint);
+        }
+        p.sweep_groups = groups; p.sweep_div = div; p.l2_hint = hint;
+    }
     p.n = op->n; p.n_pad = op->n_pad; p.row0 = op->row0; p.mloc = op->mloc;
     p.ld = X->ld; p.ldw = W->ld;
     p.sigma2 = op->sigma2; p.nugget = op->nugget; p.beta = op->beta;
