@@ -145,7 +145,7 @@ static bool op_symmetric(const gsi_op* op) { return op->type != OP_DENSE; }
 static void normalise_lu(gsi_op* op, gsi_buf* Y, bool sharded) {
     gsi_ctx* ctx = op->ctx;
     phase_begin(ctx);
-    struct End { gsi_ctx* c; ~End() { phase_end(c, PH_LU); } } end_{ctx};
+    struct End { gsi_ctx* c; ~End() { try { phase_end(c, PH_LU); } catch (...) {} } } end_{ctx};
     if (sharded && ctx->world > 1) {
         lu_L_inplace(ctx, Y, op->row0, op->m, op->part.data());
     } else {
@@ -161,7 +161,7 @@ static void normalise_lu(gsi_op* op, gsi_buf* Y, bool sharded) {
 void tsqr_thinQ(gsi_op* op, gsi_buf* Y, bool sharded, double* Rdev) {
     gsi_ctx* ctx = op->ctx;
     phase_begin(ctx);
-    struct End { gsi_ctx* c; ~End() { phase_end(c, PH_QR); } } end_{ctx};
+    struct End { gsi_ctx* c; ~End() { try { phase_end(c, PH_QR); } catch (...) {} } } end_{ctx};
     const int l = (int)Y->cols;
     if (!(sharded && ctx->world > 1)) {
         qr_thinQ_inplace(ctx, Y, Rdev);
