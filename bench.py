@@ -275,10 +275,18 @@ def main():
 
     if rank == 0:
         gemm_ms, gemm_launches, gemm_flops = gemm
+        traffic = None
+        try:
+            with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+                tj = json.load(f)
+            if world == 1 and args.generation == "table" and args.workload in tj:
+                traffic = tj[args.workload]["bytes_per_launch"]      # from the committed ncu capture
+        except Exception:
+            traffic = None
         ach = gemm_flops / (gemm_ms * 1e-3) * 1e-12 if gemm_ms > 0 else None
         roof = {"bound": "tensor", "kernel": "kcov_gemm_kernel (matrix-free covariance x tall-skinny, DMMA.8x8x4)",
                 "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": (ach / peak) if ach else None,
-                "traffic": None,
+                "traffic": traffic,
                 "peak_source": "cuBLAS DGEMM 8192^3 (torch.matmul fp64) best of 5 measured in this run; "
                                "MEASURED_PEAKS.json has no FP64 entry",
                 "avg_launch_ms": gemm_ms / max(gemm_launches, 1), "launches_timed": gemm_launches,

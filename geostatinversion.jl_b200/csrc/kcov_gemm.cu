@@ -185,11 +185,14 @@ __global__ void __launch_bounds__(KC_THREADS, 1) kcov_gemm_kernel(const __grid_c
         return full_rounds * per_round + b0;
     };
     const int64_t nkt = (p.n + KC_BK - 1) / KC_BK;
-    // Optional de-synchronised (cyclic) k sweeps, GSI_SWEEP="groups,div,hint": CTA b starts its sweep
-    // (b mod groups) * nkt/div tiles into X.  Measured on C3 (profiles/r01): 64 groups over a quarter
-    // of X gives +2.5 % (31.8 vs 31.0 TF/s) but the L2 hit rate of the X stream falls from 98 % to
-    // 26 % and the launch re-reads ~700 GB from HBM instead of 8.6 GB; small separations that keep
-    // the stream L2-resident give no gain.  Default: lock-step sweeps (groups = 1).
+    // De-synchronised (cyclic) k sweeps, GSI_SWEEP="groups,div,hint": CTA b starts its sweep
+    // (b mod groups) * nkt/div tiles into X (default 64 groups over a quarter of X).  Measured on C3
+    // (profiles/r01): +2.5 % over lock-step sweeps (31.8 vs 31.0 TF/s); requests for one X tile no
+    // longer arrive from all 148 SMs at once.  Either way the X stream (366 MB > L2) is served
+    // mostly from HBM once the persistent CTAs have drifted apart: ncu shows ~715 GB read per launch
+    // (L2 hit rate 27 %, 16 % of HBM bandwidth) with the DMMA pipe 91-93 % busy.  Forcing L2
+    // residency (k-chunks of 48 MB with a W read-modify-write per chunk) cost 9-22 % of tensor
+    // throughput and was not kept; cluster multicast of the X tiles is the planned fix.
     const int64_t kt_sep = nkt >= p.sweep_div ? nkt / p.sweep_div : (nkt >= 16 ? 1 : 0);
     const int64_t kt0 = (int64_t)(blockIdx.x & (p.sweep_groups - 1)) * kt_sep;
     const uint64_t xpolicy = l2_policy_evict_last();
@@ -465,7 +468,7 @@ void kcov_apply(gsi_op* op, const gsi_buf* X, gsi_buf* W) {
         static int groups = -1, div = -1, hint = -1;
         if (groups < 0) {
             const char* e = getenv("GSI_SWEEP");     // "groups,div,hint" (tuning knob; defaults below)
-            groups = 1; div = 256; hint = 0;
+            groups = 64; div = 256; hint = 0;
             if (e) sscanf(e, "%d,%d,%d", &groups, &div, &hint);
         }
         p.sweep_groups = groups; p.sweep_div = div; p.l2_hint = hint;
