@@ -194,7 +194,7 @@ __global__ void __launch_bounds__(KC_THREADS, 1) kcov_gemm_kernel(const __grid_c
     // residency (k-chunks of 48 MB with a W read-modify-write per chunk) cost 9-22 % of tensor
     // throughput and was not kept; cluster multicast of the X tiles is the planned fix.
     const int64_t kt_sep = nkt >= p.sweep_div ? nkt / p.sweep_div : (nkt >= 16 ? 1 : 0);
-    const int64_t kt0 = (int64_t)(blockIdx.x & (p.sweep_groups - 1)) * kt_sep;
+    const int64_t kt0 = ((int64_t)(blockIdx.x & (p.sweep_groups - 1)) * kt_sep) % nkt;
     const uint64_t xpolicy = l2_policy_evict_last();
     constexpr uint32_t stage_bytes = (uint32_t)(KC_BK * ld * sizeof(double) +
                                                 DIM * KC_BK * (KIND == KC_KIND_TABLE ? sizeof(int) : sizeof(double)));
