@@ -25,14 +25,18 @@ BufPtr make_buf(gsi_ctx* ctx, int32_t layout, int64_t rows, int64_t cols) {
         throw Error(GSI_ERR_INVALID_ARGUMENT, "unknown buffer layout");
     }
     b->d = static_cast<double*>(pool_alloc(ctx, b->bytes()));
+    ctx_retain(ctx);
     GSI_CUDA(cudaMemsetAsync(b->d, 0, b->bytes(), ctx->stream));
     return b;
 }
 
 void BufDeleter::operator()(gsi_buf* b) const {
     if (!b) return;
-    if (b->owns && b->d) pool_free(b->ctx, b->d, b->bytes());
+    gsi_ctx* bctx = b->ctx;
+    const bool owned = b->owns && b->d;
+    if (owned) pool_free(bctx, b->d, b->bytes());
     delete b;
+    if (owned) ctx_release(bctx);
 }
 
 // ------------------------------------------------------------------ operator application

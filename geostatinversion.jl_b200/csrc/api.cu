@@ -126,20 +126,47 @@ GSI_API int32_t gsi_ctx_create(int32_t device, int32_t rank, int32_t world, cons
     });
 }
 
+static void ctx_really_destroy(gsi_ctx* ctx) {
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    comm_destroy(ctx);
+    pool_release(ctx);
+    if (ctx->scratch) cudaFree(ctx->scratch);
+    if (ctx->dflags) cudaFree(ctx->dflags);
+    if (ctx->ev0) cudaEventDestroy(ctx->ev0);
+    if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+    for (cudaEvent_t e : ctx->ev_pool) cudaEventDestroy(e);
+    if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+namespace gsi {
+static std::mutex g_ctx_mutex;
+void ctx_retain(gsi_ctx* ctx) {
+    std::lock_guard<std::mutex> lock(g_ctx_mutex);
+    ++ctx->live_objects;
+}
+void ctx_release(gsi_ctx* ctx) {
+    bool kill = false;
+    {
+        std::lock_guard<std::mutex> lock(g_ctx_mutex);
+        --ctx->live_objects;
+        kill = ctx->destroy_requested && ctx->live_objects <= 0;
+    }
+    if (kill) ctx_really_destroy(ctx);
+}
+}  // namespace gsi
+
 GSI_API int32_t gsi_ctx_destroy(gsi_ctx* ctx) {
     return guarded([&] {
         if (!ctx) return;
-        cudaSetDevice(ctx->device);
-        cudaStreamSynchronize(ctx->stream);
-        comm_destroy(ctx);
-        pool_release(ctx);
-        if (ctx->scratch) cudaFree(ctx->scratch);
-        if (ctx->dflags) cudaFree(ctx->dflags);
-        if (ctx->ev0) cudaEventDestroy(ctx->ev0);
-        if (ctx->ev1) cudaEventDestroy(ctx->ev1);
-        for (cudaEvent_t e : ctx->ev_pool) cudaEventDestroy(e);
-        if (ctx->stream) cudaStreamDestroy(ctx->stream);
-        delete ctx;
+        bool now = false;
+        {
+            std::lock_guard<std::mutex> lock(g_ctx_mutex);
+            ctx->destroy_requested = true;
+            now = ctx->live_objects <= 0;
+        }
+        if (now) ctx_really_destroy(ctx);      // otherwise the last buffer / operator release does it
     });
 }
 
@@ -291,6 +318,7 @@ GSI_API int32_t gsi_op_dense(gsi_ctx* ctx, gsi_buf* A_local, int64_t row0, int64
         op->ctx = ctx; op->type = OP_DENSE; op->A = A_local;
         op->m = m_global; op->n = A_local->cols; op->row0 = row0; op->mloc = A_local->rows;
         set_partition(op.get());
+        ctx_retain(ctx);
         *out = op.release();
     });
 }
@@ -321,6 +349,7 @@ GSI_API int32_t gsi_op_lowrankcov(gsi_ctx* ctx, gsi_buf* samples, int32_t remove
             count_launch(ctx);
         }
         set_partition(op.get());
+        ctx_retain(ctx);
         *out = op.release();
     });
 }
@@ -353,6 +382,7 @@ GSI_API int32_t gsi_op_kernelcov(gsi_ctx* ctx, int32_t kind, int32_t d, int64_t 
         GSI_CUDA(cudaMemcpyAsync(op->ucoords, u.data(), u.size() * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
         GSI_CUDA(cudaStreamSynchronize(ctx->stream));
         set_partition(op.get());
+        ctx_retain(ctx);
         *out = op.release();
     });
 }
@@ -410,6 +440,7 @@ GSI_API int32_t gsi_op_kernelcov_grid(gsi_ctx* ctx, int32_t kind, int32_t d, con
         GSI_CUDA(cudaMemcpyAsync(op->lattice, lat.data(), lat.size() * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
         GSI_CUDA(cudaStreamSynchronize(ctx->stream));
         set_partition(op.get());
+        ctx_retain(ctx);
         *out = op.release();
     });
 }
@@ -422,7 +453,9 @@ GSI_API int32_t gsi_op_free(gsi_op* op) {
         if (op->table) cudaFree(op->table);
         if (op->lattice) cudaFree(op->lattice);
         if (op->tmpT) BufDeleter()(op->tmpT);
+        gsi_ctx* octx = op->ctx;
         delete op;
+        ctx_release(octx);
     });
 }
 

@@ -59,6 +59,10 @@ struct gsi_ctx {
     double* scratch = nullptr;           // doubles
     size_t scratch_doubles = 0;
     int* dflags = nullptr;               // device int flags [16]
+    // buffers / operators alive on this context; gsi_ctx_destroy is deferred until they are gone
+    // (Julia finalizers and Python interpreter shutdown run in no particular order)
+    int64_t live_objects = 0;
+    bool destroy_requested = false;
     // launch counter (kernels launched by this library since last reset)
     int64_t launches = 0;
     // optional event pair around the dominant GEMM kernel (bench roofline)
@@ -160,5 +164,7 @@ void phase_end(gsi_ctx*, int phase);
 void* pool_alloc(gsi_ctx*, size_t bytes);
 void pool_free(gsi_ctx*, void* p, size_t bytes);
 void pool_release(gsi_ctx*);
+void ctx_retain(gsi_ctx*);
+void ctx_release(gsi_ctx*);      // may destroy the context if gsi_ctx_destroy was already requested
 
 }  // namespace gsi

@@ -92,6 +92,20 @@ function KernelCovMatrix(kind::Integer, coords::Matrix{Float64}, ell::Vector{Flo
 	return op
 end
 
+"structured grid variant: dims[1] fastest (Julia linear index), coordinates idx .* spacing"
+function KernelCovGrid(kind::Integer, dims::Vector{Int}, spacing::Vector{Float64}, ell::Vector{Float64}; sigma2=1.0, nugget=0.0, beta=1.0, ctx::Context=context())
+	d = length(dims)
+	n = prod(dims)
+	out = Ref{Ptr{Cvoid}}(C_NULL)
+	dims64 = Int64.(dims)
+	GC.@preserve dims64 spacing ell check(ccall((:gsi_op_kernelcov_grid, LIB), Int32,
+		(Ptr{Cvoid}, Int32, Int32, Ptr{Int64}, Ptr{Float64}, Ptr{Float64}, Float64, Float64, Float64, Int64, Int64, Ref{Ptr{Cvoid}}),
+		ctx.h, kind, d, dims64, spacing, ell, sigma2, nugget, beta, 0, n, out))
+	op = KernelCovMatrix(out[], n, ctx)
+	finalizer(o->ccall((:gsi_op_free, LIB), Int32, (Ptr{Cvoid},), o.h), op)
+	return op
+end
+
 function LowRankCovMatrix(samples::Vector{Vector{Float64}}; ctx::Context=context())
 	S = reduce(hcat, samples)
 	buf = upload!(DeviceMatrix(ctx, GSI_LAYOUT_COLMAJOR, size(S)...), S)
