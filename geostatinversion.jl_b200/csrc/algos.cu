@@ -172,9 +172,10 @@ void tsqr_thinQ(gsi_op* op, gsi_buf* Y, bool sharded, double* Rdev) {
         return;
     }
     const int G = ctx->world;
-    double* Rall = nullptr;                      // [G][l*l] column-major blocks
-    GSI_CUDA(cudaMalloc(&Rall, (size_t)(G + 1) * l * l * sizeof(double)));
-    std::unique_ptr<double, void (*)(double*)> guard(Rall, [](double* p) { cudaFree(p); });
+    // [G][l*l] column-major blocks (+ my own), from the pooled allocator (no cudaMalloc/cudaFree sync)
+    const size_t rall_bytes = (size_t)(G + 1) * l * l * sizeof(double);
+    double* Rall = static_cast<double*>(pool_alloc(ctx, rall_bytes));
+    struct PoolGuard { gsi_ctx* c; void* p; size_t b; ~PoolGuard() { pool_free(c, p, b); } } guard{ctx, Rall, rall_bytes};
     double* Rmine = Rall + (size_t)G * l * l;
     // a rank that owns fewer than l rows factors its block padded with zero rows (same R)
     BufPtr padded;
@@ -321,9 +322,9 @@ void randsvd(gsi_op* op, const gsi_buf* Omega, int64_t K, int64_t p, int64_t q, 
     Q.buf.reset();
     full_scratch.reset();
     // svd(B) (:86): B' = Q_B R_B,  R_B = U_R S V_R'  =>  V = Q_B U_R
-    double* small = nullptr;                                             // R | U | sigma | Usc
-    GSI_CUDA(cudaMalloc(&small, ((size_t)3 * l * l + l) * sizeof(double)));
-    std::unique_ptr<double, void (*)(double*)> guard(small, [](double* ptr) { cudaFree(ptr); });
+    const size_t small_bytes = ((size_t)3 * l * l + l) * sizeof(double);   // R | U | Usc | sigma
+    double* small = static_cast<double*>(pool_alloc(ctx, small_bytes));
+    struct PoolGuard { gsi_ctx* c; void* p; size_t b; ~PoolGuard() { pool_free(c, p, b); } } guard{ctx, small, small_bytes};
     double* R = small;
     double* U = small + (size_t)l * l;
     double* Usc = small + (size_t)2 * l * l;
