@@ -50,6 +50,8 @@ SIGNATURES = {
     "gsi_ctx_launch_count": (_i32, [_p, _pi64, _i32]),
     "gsi_ctx_gemm_timing": (_i32, [_p, _i32, _pd, _pi64, _pd]),
     "gsi_ctx_phase_timing": (_i32, [_p, _pd, _i32]),
+    "gsi_ctx_set_option": (_i32, [_p, C.c_char_p, _i64]),
+    "gsi_ctx_get_option": (_i32, [_p, C.c_char_p, _pi64]),
     "gsi_buf_alloc": (_i32, [_p, _i32, _i64, _i64, _pp]),
     "gsi_buf_free": (_i32, [_p]),
     "gsi_buf_dims": (_i32, [_p, _pi64, _pi64]),

@@ -76,6 +76,15 @@ class Context:
         names = ["products", "lu", "qr", "svd_small", "backmul"]
         return {n: out[i] for i, n in enumerate(names)}
 
+    def set_option(self, name, value):
+        """Tuning knob (gsi_ctx_set_option), e.g. ("kcov.window", 8)."""
+        check(self._lib.gsi_ctx_set_option(self._h, name.encode(), int(value)))
+
+    def get_option(self, name):
+        v = C.c_int64()
+        check(self._lib.gsi_ctx_get_option(self._h, name.encode(), C.byref(v)))
+        return v.value
+
     def close(self):
         if getattr(self, "_h", None) and self._h:
             self._lib.gsi_ctx_destroy(self._h)

@@ -75,6 +75,16 @@ void pool_release(gsi_ctx* ctx) {
     ctx->cached_bytes = 0;
 }
 
+static void validate_kcov_options(const gsi_ctx* ctx) {
+    const int g = ctx->kcov_sweep_groups;
+    GSI_REQUIRE(g >= 1 && g <= 1024 && (g & (g - 1)) == 0, GSI_ERR_INVALID_ARGUMENT,
+                "kcov.sweep_groups must be a power of two in [1, 1024]");
+    GSI_REQUIRE(ctx->kcov_window >= 0 && ctx->kcov_window <= 4096, GSI_ERR_INVALID_ARGUMENT,
+                "kcov.window must be in [0, 4096] epochs");
+    GSI_REQUIRE(ctx->kcov_epoch_shift >= 2 && ctx->kcov_epoch_shift <= 16, GSI_ERR_INVALID_ARGUMENT,
+                "kcov.epoch_shift must be in [2, 16]");
+}
+
 static void use(gsi_ctx* ctx) {
     GSI_REQUIRE(ctx != nullptr, GSI_ERR_INVALID_ARGUMENT, "null context");
     GSI_CUDA(cudaSetDevice(ctx->device));
@@ -121,6 +131,10 @@ GSI_API int32_t gsi_ctx_create(int32_t device, int32_t rank, int32_t world, cons
         GSI_CUDA(cudaMemset(ctx->dflags, 0, 16 * sizeof(int)));
         GSI_CUDA(cudaEventCreate(&ctx->ev0));
         GSI_CUDA(cudaEventCreate(&ctx->ev1));
+        if (const char* e = getenv("GSI_SWEEP"))      // "groups,div,hint[,window[,epoch_shift]]": see gsi_ctx_set_option
+            sscanf(e, "%d,%d,%d,%d,%d", &ctx->kcov_sweep_groups, &ctx->kcov_sweep_div, &ctx->kcov_l2_hint,
+                   &ctx->kcov_window, &ctx->kcov_epoch_shift);
+        validate_kcov_options(ctx.get());
         if (world > 1) comm_init(ctx.get(), unique_id128);
         *out = ctx.release();
     });
@@ -133,6 +147,7 @@ static void ctx_really_destroy(gsi_ctx* ctx) {
     pool_release(ctx);
     if (ctx->scratch) cudaFree(ctx->scratch);
     if (ctx->dflags) cudaFree(ctx->dflags);
+    if (ctx->sweep_cnt) cudaFree(ctx->sweep_cnt);
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
     for (cudaEvent_t e : ctx->ev_pool) cudaEventDestroy(e);
@@ -167,6 +182,44 @@ GSI_API int32_t gsi_ctx_destroy(gsi_ctx* ctx) {
             now = ctx->live_objects <= 0;
         }
         if (now) ctx_really_destroy(ctx);      // otherwise the last buffer / operator release does it
+    });
+}
+
+GSI_API int32_t gsi_ctx_set_option(gsi_ctx* ctx, const char* name, int64_t value) {
+    return guarded([&] {
+        use(ctx);
+        GSI_REQUIRE(name != nullptr, GSI_ERR_INVALID_ARGUMENT, "null option name");
+        const std::string n(name);
+        const int v = (int)value;
+        const int saved[5] = {ctx->kcov_sweep_groups, ctx->kcov_sweep_div, ctx->kcov_l2_hint, ctx->kcov_window,
+                              ctx->kcov_epoch_shift};
+        if (n == "kcov.sweep_groups") ctx->kcov_sweep_groups = v;
+        else if (n == "kcov.sweep_div") ctx->kcov_sweep_div = v;
+        else if (n == "kcov.l2_hint") ctx->kcov_l2_hint = v;
+        else if (n == "kcov.window") ctx->kcov_window = v;
+        else if (n == "kcov.epoch_shift") ctx->kcov_epoch_shift = v;
+        else throw Error(GSI_ERR_INVALID_ARGUMENT, "unknown option '" + n + "'");
+        try {
+            validate_kcov_options(ctx);
+        } catch (...) {
+            ctx->kcov_sweep_groups = saved[0]; ctx->kcov_sweep_div = saved[1]; ctx->kcov_l2_hint = saved[2];
+            ctx->kcov_window = saved[3]; ctx->kcov_epoch_shift = saved[4];
+            throw;
+        }
+    });
+}
+
+GSI_API int32_t gsi_ctx_get_option(gsi_ctx* ctx, const char* name, int64_t* value_out) {
+    return guarded([&] {
+        use(ctx);
+        GSI_REQUIRE(name != nullptr && value_out != nullptr, GSI_ERR_INVALID_ARGUMENT, "null argument");
+        const std::string n(name);
+        if (n == "kcov.sweep_groups") *value_out = ctx->kcov_sweep_groups;
+        else if (n == "kcov.sweep_div") *value_out = ctx->kcov_sweep_div;
+        else if (n == "kcov.l2_hint") *value_out = ctx->kcov_l2_hint;
+        else if (n == "kcov.window") *value_out = ctx->kcov_window;
+        else if (n == "kcov.epoch_shift") *value_out = ctx->kcov_epoch_shift;
+        else throw Error(GSI_ERR_INVALID_ARGUMENT, "unknown option '" + n + "'");
     });
 }
 

@@ -81,6 +81,14 @@ struct gsi_ctx {
     // cost milliseconds and synchronise the device, so freed blocks are kept for reuse
     std::vector<std::pair<size_t, void*>> free_blocks;
     size_t cached_bytes = 0;
+    // k-sweep schedule of the matrix-free product kernel (kcov_gemm.cu; gsi_ctx_set_option "kcov.*")
+    int kcov_sweep_groups = 64;          // CTAs start their sweep at (b mod groups) * separation tiles
+    int kcov_sweep_div = 256;            // separation = nkt / div tiles (div > 0) or -div tiles (div < 0)
+    int kcov_l2_hint = 0;                // evict_last cache hint on the X stream
+    int kcov_window = 0;                 // epochs a CTA may run ahead of the slowest CTA (0: unthrottled)
+    int kcov_epoch_shift = 6;            // epoch = 2^shift k-tiles
+    unsigned int* sweep_cnt = nullptr;   // per-epoch arrival counters of one launch
+    size_t sweep_cnt_n = 0;
 };
 
 struct gsi_buf {

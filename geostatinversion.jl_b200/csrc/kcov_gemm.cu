@@ -33,6 +33,7 @@ constexpr int KC_WARPS = 16;
 constexpr int KC_THREADS = KC_WARPS * 32;
 constexpr int KC_CG = 4;           // column groups (warps sharing one row group)
 constexpr int KC_KIND_TABLE = 3;   // internal kind: stationary kernel on a structured grid, values from a lattice table
+constexpr long long KC_SPIN_LIMIT = 400000;   // cycles (~0.2 ms) a producer waits on the sweep window before giving it up
 
 struct KcovParams {
     const double* X;       // TALL, all n rows (zero padded), pitch ld
@@ -42,6 +43,8 @@ struct KcovParams {
     const double* table;   // k(r2) for every lattice offset: table[dx + nx*(dy + ny*dz)]
     int nx, ny;
     int sweep_groups, sweep_div, l2_hint;   // k-sweep de-synchronisation (power-of-two groups, spread = groups/div of X)
+    unsigned int* sync_cnt;                 // sweep window: arrivals per epoch (zeroed before the launch)
+    int win_epochs, epoch_shift;            // a CTA runs at most win_epochs epochs of 2^epoch_shift k-tiles ahead of the slowest
     int64_t n;             // columns of C (= rows of X)
     int64_t n_pad;
     int64_t row0;          // first global row of this rank's block
@@ -193,8 +196,22 @@ __global__ void __launch_bounds__(KC_THREADS, 1) kcov_gemm_kernel(const __grid_c
     // (L2 hit rate 27 %, 16 % of HBM bandwidth) with the DMMA pipe 91-93 % busy.  Forcing L2
     // residency (k-chunks of 48 MB with a W read-modify-write per chunk) cost 9-22 % of tensor
     // throughput and was not kept; cluster multicast of the X tiles is the planned fix.
-    const int64_t kt_sep = nkt >= p.sweep_div ? nkt / p.sweep_div : (nkt >= 16 ? 1 : 0);
+    const int64_t kt_sep = p.sweep_div < 0 ? -(int64_t)p.sweep_div
+                           : p.sweep_div == 0 ? 0
+                           : (nkt >= p.sweep_div ? nkt / p.sweep_div : (nkt >= 16 ? 1 : 0));
     const int64_t kt0 = ((int64_t)(blockIdx.x & (p.sweep_groups - 1)) * kt_sep) % nkt;
+    // Sweep window (p.win_epochs > 0): the persistent CTAs all stream the same X, but left alone they
+    // drift apart by more than an L2's worth of k-tiles and every CTA ends up streaming X from HBM
+    // (ncu: 716 GB per C3 launch against 0.7 GB algorithmic).  The schedule is static -- the launch
+    // ends with its slowest CTA anyway -- so the producer holds a CTA that is more than win_epochs
+    // epochs ahead of the slowest one: every 2^epoch_shift k-tiles it counts itself into the epoch's
+    // arrival counter and waits until the epoch win_epochs back has been reached by every CTA that
+    // will ever reach it (all CTAs during the full rounds, the tail CTAs afterwards).  The wait is
+    // bounded (KC_SPIN_LIMIT): a CTA that times out -- co-tenancy, a debugger -- drops the window
+    // for the rest of the launch, so the window can cost time but never progress.
+    const int64_t full_it = full_rounds * nkt;
+    const unsigned n_tail_ctas = q_tail > 0 ? (unsigned)((remaining + q_tail - 1) / q_tail) : 0u;
+    bool window_on = p.win_epochs > 0;            // thread 0 only
     const uint64_t xpolicy = l2_policy_evict_last();
     constexpr uint32_t stage_bytes = (uint32_t)(KC_BK * ld * sizeof(double) +
                                                 DIM * KC_BK * (KIND == KC_KIND_TABLE ? sizeof(int) : sizeof(double)));
@@ -207,6 +224,19 @@ __global__ void __launch_bounds__(KC_THREADS, 1) kcov_gemm_kernel(const __grid_c
         const uint32_t ph = (uint32_t)((nxt / nstages) & 1);
         int64_t kt = nxt % nkt + kt0;
         if (kt >= nkt) kt -= nkt;
+        if (p.win_epochs > 0 && (nxt & (((int64_t)1 << p.epoch_shift) - 1)) == 0) {
+            const int64_t e = nxt >> p.epoch_shift;
+            atomicAdd(p.sync_cnt + e, 1u);
+            const int64_t ew = e - p.win_epochs;
+            if (window_on && ew >= 0) {
+                const unsigned target = ((ew << p.epoch_shift) < full_it) ? gridDim.x : n_tail_ctas;
+                const volatile unsigned int* c = p.sync_cnt + ew;
+                const long long t0 = clock64();
+                while (*c < target) {
+                    if (clock64() - t0 > KC_SPIN_LIMIT) { window_on = false; break; }
+                }
+            }
+        }
         mbar_wait(&empty[s], ph ^ 1u);
         double* xs = smem + (size_t)s * stage_doubles;
         double* us = xs + KC_BK * ld;
@@ -429,6 +459,23 @@ static void launch_kcov(gsi_ctx* ctx, const KcovParams& p0) {
     int64_t grid = (int64_t)ctx->num_sms * occ;
     if (grid > total_rg) grid = total_rg;
     if (grid < 1) grid = 1;
+    p.win_epochs = ctx->kcov_window > 0 ? ctx->kcov_window : 0;
+    p.epoch_shift = ctx->kcov_epoch_shift;
+    p.sync_cnt = nullptr;
+    if (p.win_epochs > 0) {
+        // one arrival counter per epoch of the longest CTA schedule (full rounds + tail round)
+        const int64_t nkt = (p.n + KC_BK - 1) / KC_BK;
+        const int64_t rounds = total_rg / (grid * 4) + (total_rg % (grid * 4) != 0 ? 1 : 0);
+        const size_t n_epochs = (size_t)((rounds * nkt) >> p.epoch_shift) + 2;
+        if (n_epochs > ctx->sweep_cnt_n) {
+            if (ctx->sweep_cnt) GSI_CUDA(cudaFree(ctx->sweep_cnt));
+            ctx->sweep_cnt = nullptr; ctx->sweep_cnt_n = 0;
+            GSI_CUDA(cudaMalloc(&ctx->sweep_cnt, n_epochs * sizeof(unsigned int)));
+            ctx->sweep_cnt_n = n_epochs;
+        }
+        GSI_CUDA(cudaMemsetAsync(ctx->sweep_cnt, 0, n_epochs * sizeof(unsigned int), ctx->stream));
+        p.sync_cnt = ctx->sweep_cnt;
+    }
     kfn<<<(unsigned)grid, KC_THREADS, smem, ctx->stream>>>(p);
     GSI_CUDA(cudaGetLastError());
     count_launch(ctx);
@@ -464,15 +511,7 @@ void kcov_apply(gsi_op* op, const gsi_buf* X, gsi_buf* W) {
     KcovParams p;
     p.X = X->d; p.W = W->d; p.u = op->ucoords;
     p.lat = op->lattice; p.table = op->table; p.nx = op->grid_nx; p.ny = op->grid_ny;
-    {
-        static int groups = -1, div = -1, hint = -1;
-        if (groups < 0) {
-            const char* e = getenv("GSI_SWEEP");     // "groups,div,hint" (tuning knob; defaults below)
-            groups = 64; div = 256; hint = 0;
-            if (e) sscanf(e, "%d,%d,%d", &groups, &div, &hint);
-        }
-        p.sweep_groups = groups; p.sweep_div = div; p.l2_hint = hint;
-    }
+    p.sweep_groups = ctx->kcov_sweep_groups; p.sweep_div = ctx->kcov_sweep_div; p.l2_hint = ctx->kcov_l2_hint;
     p.n = op->n; p.n_pad = op->n_pad; p.row0 = op->row0; p.mloc = op->mloc;
     p.ld = X->ld; p.ldw = W->ld;
     p.sigma2 = op->sigma2; p.nugget = op->nugget; p.beta = op->beta;

@@ -100,6 +100,20 @@ int32_t gsi_ctx_gemm_timing(gsi_ctx* ctx, int32_t enable, double* ms_out, int64_
  * [1] LU normaliser, [2] QR/TSQR, [3] small SVD, [4] back-multiplication; [5..7] reserved. */
 int32_t gsi_ctx_phase_timing(gsi_ctx* ctx, double* ms_out8, int32_t reset);
 
+/* Tuning knobs (no reference counterpart; results do not depend on them beyond rounding-
+ * identical reordering of WHEN tiles are read).  Names:
+ *   "kcov.sweep_groups"  power of two: CTA b of the matrix-free product kernel starts its
+ *                        k sweep (b mod groups) * separation tiles into X
+ *   "kcov.sweep_div"     separation = (#k-tiles / div) if div > 0, (-div) tiles if div < 0
+ *   "kcov.l2_hint"       1: evict_last cache hint on the X stream
+ *   "kcov.window"        > 0: a CTA runs at most this many epochs ahead of the slowest CTA,
+ *                        which keeps the shared X stream L2-resident; 0: unthrottled
+ *   "kcov.epoch_shift"   epoch = 2^shift k-tiles of 32 points
+ * The environment variable GSI_SWEEP="groups,div,hint[,window[,epoch_shift]]" sets the
+ * same knobs at context creation.                                                     */
+int32_t gsi_ctx_set_option(gsi_ctx* ctx, const char* name, int64_t value);
+int32_t gsi_ctx_get_option(gsi_ctx* ctx, const char* name, int64_t* value_out);
+
 /* ---- device buffers (replace Julia `Matrix{Float64}` temporaries) ----------------- */
 int32_t gsi_buf_alloc(gsi_ctx* ctx, int32_t layout, int64_t rows, int64_t cols, gsi_buf** out);
 int32_t gsi_buf_free(gsi_buf* buf); /* idempotent on NULL, never throws (Julia finalizer) */

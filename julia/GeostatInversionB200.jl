@@ -39,6 +39,15 @@ mutable struct Context
 	end
 end
 
+# tuning knobs of include/gsi_b200.h (gsi_ctx_set_option), e.g. setoption!(ctx, "kcov.window", 8)
+setoption!(ctx::Context, name::AbstractString, value::Integer) =
+	check(ccall((:gsi_ctx_set_option, LIB), Int32, (Ptr{Cvoid}, Cstring, Int64), ctx.h, name, value))
+function getoption(ctx::Context, name::AbstractString)
+	v = Ref{Int64}(0)
+	check(ccall((:gsi_ctx_get_option, LIB), Int32, (Ptr{Cvoid}, Cstring, Ref{Int64}), ctx.h, name, v))
+	return v[]
+end
+
 const defaultctx = Ref{Union{Nothing, Context}}(nothing)
 context() = (defaultctx[] === nothing && (defaultctx[] = Context()); defaultctx[])
 

@@ -174,3 +174,39 @@ def test_lowrankcov_vs_oracle(gsi):
     X = rng.standard_normal((n, l))
     ref = oracle.LowRankCovMatrix(fields) @ X
     assert relerr(gsi.LowRankCovMatrix(fields) @ X, ref) < 1e-12
+
+
+@pytest.mark.parametrize("table", [True, False])
+def test_kernelcov_sweep_window(gsi, table):
+    """The sweep window (gsi_ctx_set_option "kcov.window") only changes WHEN a CTA reads an X
+    tile, never the order it accumulates them in: products are bit-identical with the window on
+    and off, and match the dense oracle on sampled rows (1e-12).  Sized so that the persistent
+    grid runs one full round plus a tail round (n > 64 * 148) with many 4-tile epochs."""
+    ctx = gsi.default_context()
+    grid, ell, l = (110, 109), [7.0, 5.0], 24
+    coords = oracle.grid_coords(grid)
+    n = coords.shape[1]
+    X = np.random.default_rng(5).standard_normal((n, l))
+    if table:
+        op = gsi.GridKernelCovMatrix("exponential", grid, ell)
+    else:
+        op = gsi.KernelCovMatrix("exponential", coords, ell)
+    saved = {k: ctx.get_option(k) for k in ("kcov.window", "kcov.epoch_shift", "kcov.sweep_div")}
+    try:
+        ctx.set_option("kcov.window", 0)
+        ctx.set_option("kcov.sweep_div", -1)          # one tile between neighbouring sweep starts
+        Y0 = op @ X
+        ctx.set_option("kcov.epoch_shift", 2)
+        for window in (1, 3):
+            ctx.set_option("kcov.window", window)
+            assert np.array_equal(op @ X, Y0)
+    finally:
+        for k, v in saved.items():
+            ctx.set_option(k, v)
+    rows = np.random.default_rng(6).choice(n, 200, replace=False)
+    Cr = oracle.kernel_cov_dense(0, coords, ell, rows=rows)
+    assert relerr(Y0[rows], Cr @ X) < 1e-12
+    with pytest.raises(gsi.GsiError):
+        ctx.set_option("kcov.sweep_groups", 3)
+    with pytest.raises(gsi.GsiError):
+        ctx.set_option("no.such.option", 1)
