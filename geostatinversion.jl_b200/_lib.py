@@ -78,6 +78,7 @@ SIGNATURES = {
     "gsi_pcga_lowrank_matvec": (_i32, [_p, _i64, _i64, _pd, _i64, _pd, _pd, _pd, _i64, _pd, _pd]),
     "gsi_pcga_lsqr_solve": (_i32, [_p, _i64, _i64, _pd, _i64, _pd, _pd, _pd, _i64, _pd, _f64, _f64, _f64,
                                    _i64, _pd, _pi64, _pi32]),
+    "gsi_pcga_direct_solve": (_i32, [_p, _i64, _i64, _pd, _i64, _pd, _pd, _pd, _i64, _pd, _pd, _pi64]),
     "gsi_pcga_update": (_i32, [_p, _p, _i64, _pd, _pd, _i64, _i64, _pd, _pd]),
     "gsi_pcga_paramstorun": (_i32, [_p, _p, _i64, _pd, _pd, _f64, _p]),
     "gsi_sketch_apply": (_i32, [_p, _p, _p, _p]),

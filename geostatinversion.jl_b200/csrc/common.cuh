@@ -153,6 +153,9 @@ void qr_thinQ_inplace(gsi_ctx*, gsi_buf* Y, double* Rdev /* l*l or null */);
 // ---- svd.cu : one-sided Jacobi on l x l column-major device matrix M (overwritten with U),
 //      sigma (device, l) sorted descending, columns of U permuted accordingly
 void svd_small(gsi_ctx*, double* M, int l, double* U, double* sigma);
+//      the sweeps alone, on the first rows_dot rows of ncols columns (pitch ld); rotations are applied
+//      to all rows_all rows (rows below rows_dot accumulate the right singular vectors)
+void jacobi_sweeps(gsi_ctx*, double* M, int64_t ld, int rows_dot, int rows_all, int ncols);
 // ---- comm.cu
 void comm_allgather(gsi_ctx*, const void* send, void* recv, size_t bytes_per_rank);
 void comm_allreduce_sum(gsi_ctx*, double* buf, size_t count);

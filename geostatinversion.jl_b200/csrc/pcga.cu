@@ -6,6 +6,9 @@
 //   * the parameter update s = X*beta + sum_i xi_i * dot(eta_i, xi_bar) (src/lsqr.jl:55-61)
 //   * the `paramstorun` batch (src/lsqr.jl:37-43)
 //   * rga's sketch products S*V and S*R*S' (src/GeostatInversion.jl:102) on the DMMA GEMM.
+//   * pcgadirect's dense solve (reference src/direct.jl:49-58): HQH = E E' on the DMMA GEMM,
+//     x = pinv([HQH + R, HX; HX', 0]) b by one-sided Jacobi with accumulated right vectors and
+//     Julia's pinv cut-off.
 #include "common.cuh"
 #include "algos.h"
 
@@ -280,6 +283,75 @@ __global__ void scaled_transpose_kernel(const double* __restrict__ S, int64_t ld
     }
 }
 
+// ---- pcgadirect: saddle-point matrix and pseudo-inverse solve (reference src/direct.jl:49-58)
+// Columns [c0, c0+nc) of the top-left block of M (column-major, pitch ldm): HQH + R, where
+// O (TALL nobs x nc) holds HQH[:, c0:c0+nc].
+__global__ void saddle_block_kernel(const double* __restrict__ O, int64_t ldo, int nobs, int c0, int nc,
+                                    const double* __restrict__ Rdiag, const double* __restrict__ Rdense,
+                                    double* __restrict__ M, int64_t ldm) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;     // row (fast index of the column-major M)
+    const int c = blockIdx.y;
+    if (i >= nobs || c >= nc) return;
+    const int j = c0 + c;
+    double v = O ? O[(int64_t)i * ldo + c] : 0.0;
+    if (Rdiag) { if (i == j) v += Rdiag[i]; }
+    else v += Rdense[(int64_t)j * nobs + i];
+    M[(int64_t)j * ldm + i] = v;
+}
+// Border [.. HX; HX' 0] and the identity block below (rows m .. 2m-1) that accumulates V.
+__global__ void saddle_border_kernel(const double* __restrict__ HX, int nobs, double* __restrict__ M, int64_t ldm) {
+    const int m = nobs + 1;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= m) return;
+    M[(int64_t)i * ldm + nobs] = (i < nobs) ? HX[i] : 0.0;   // last row
+    M[(int64_t)nobs * ldm + i] = (i < nobs) ? HX[i] : 0.0;   // last column
+    M[(int64_t)i * ldm + m + i] = 1.0;                       // identity (the block was zeroed)
+}
+// After the Jacobi sweeps the top m rows of column j hold u_j * sigma_j and the bottom m rows
+// v_j:  x = sum_{sigma_j > tol} v_j (u_j' b) / sigma_j,  tol = eps * m * sigma_max  (Julia's
+// pinv default rtol = eps * min(size), atol = 0).  Single CTA; sh holds 2m doubles + LS_WARPS.
+__global__ void __launch_bounds__(LS_THREADS)
+pinv_apply_kernel(const double* __restrict__ M, int64_t ldm, int m, const double* __restrict__ b,
+                  double* __restrict__ x, int* __restrict__ rank_out) {
+    extern __shared__ double sh[];
+    double* sig2 = sh;            // m
+    double* coef = sh + m;        // m
+    double* red = sh + 2 * m;     // LS_WARPS
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int j = warp; j < m; j += LS_WARPS) {
+        const double* col = M + (int64_t)j * ldm;
+        double a = 0.0, d = 0.0;
+        for (int i = lane; i < m; i += 32) { const double v = col[i]; a += v * v; d += v * b[i]; }
+        a = ls_warp_sum(a); d = ls_warp_sum(d);
+        if (lane == 0) { sig2[j] = a; coef[j] = d; }
+    }
+    __syncthreads();
+    double mx = 0.0;
+    for (int j = threadIdx.x; j < m; j += LS_THREADS) mx = fmax(mx, sig2[j]);
+    for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    if (lane == 0) red[warp] = mx;
+    __syncthreads();
+    mx = red[0];
+    for (int w = 1; w < LS_WARPS; ++w) mx = fmax(mx, red[w]);
+    const double tol = 2.220446049250313e-16 * (double)m * sqrt(mx);
+    __syncthreads();
+    int kept = 0;
+    for (int j = threadIdx.x; j < m; j += LS_THREADS) {
+        const bool keep = sqrt(sig2[j]) > tol;
+        coef[j] = keep ? coef[j] / sig2[j] : 0.0;
+        kept += keep ? 1 : 0;
+    }
+    const double total = ls_block_sum((double)kept, red);     // (syncs: coef is complete afterwards)
+    if (threadIdx.x == 0) *rank_out = (int)(total + 0.5);
+    __syncthreads();
+    for (int i = threadIdx.x; i < m; i += LS_THREADS) {
+        const double* vrow = M + m + i;
+        double acc = 0.0;
+        for (int j = 0; j < m; ++j) acc += vrow[(int64_t)j * ldm] * coef[j];
+        x[i] = acc;
+    }
+}
+
 struct DevMem {
     gsi_ctx* ctx; void* p; size_t bytes;
     DevMem(gsi_ctx* c, size_t b) : ctx(c), p(pool_alloc(c, b ? b : 8)), bytes(b ? b : 8) {}
@@ -437,6 +509,24 @@ GSI_API int32_t gsi_sketch_apply(gsi_ctx* ctx, gsi_buf* S, const gsi_buf* V, gsi
     });
 }
 
+// O = S * diag(Rd) * S'[:, c0:c0+nc] for successive column chunks (S COLMAJOR r x c, Rd device c),
+// each handed to `consume(O, c0, nc)` as a TALL r x nc buffer.
+template <typename F>
+static void scaled_outer_chunks(gsi_ctx* ctx, gsi_buf* S, const double* Rd, F&& consume) {
+    const int64_t r = S->rows, c = S->cols;
+    for (int64_t c0 = 0; c0 < r; c0 += kMaxCols) {
+        const int64_t nc = (r - c0 < kMaxCols) ? r - c0 : kMaxCols;
+        BufPtr Xt = make_buf(ctx, GSI_LAYOUT_TALL, c, nc);          // (diag(Rd) S')[:, c0:c0+nc]
+        BufPtr O = make_buf(ctx, GSI_LAYOUT_TALL, r, nc);
+        dim3 grid((unsigned)((c + 31) / 32), (unsigned)((nc + 31) / 32)), block(32, 8);
+        scaled_transpose_kernel<<<grid, block, 0, ctx->stream>>>(S->d, S->ld, c, c0, nc, Rd, Xt->d, Xt->ld);
+        GSI_CUDA(cudaGetLastError());
+        count_launch(ctx);
+        dense_apply(ctx, S, 0, Xt.get(), O.get(), 1.0);
+        consume(O.get(), c0, nc);
+    }
+}
+
 GSI_API int32_t gsi_sketch_cov(gsi_ctx* ctx, gsi_buf* S, const double* Rdiag, double* out_host, int64_t ldo) {
     return guarded([&] {
         GSI_REQUIRE(ctx && S && Rdiag && out_host, GSI_ERR_INVALID_ARGUMENT, "null argument");
@@ -446,16 +536,63 @@ GSI_API int32_t gsi_sketch_cov(gsi_ctx* ctx, gsi_buf* S, const double* Rdiag, do
         GSI_REQUIRE(ldo >= Nred, GSI_ERR_INVALID_ARGUMENT, "sketch_cov: ldo < Nred");
         DevMem Rd(ctx, (size_t)nobs * 8);
         upload(ctx, Rd.d(), Rdiag, nobs);
-        for (int64_t c0 = 0; c0 < Nred; c0 += kMaxCols) {
-            const int64_t nc = (Nred - c0 < kMaxCols) ? Nred - c0 : kMaxCols;
-            BufPtr Xt = make_buf(ctx, GSI_LAYOUT_TALL, nobs, nc);          // (diag(R) S')[:, c0:c0+nc]
-            BufPtr O = make_buf(ctx, GSI_LAYOUT_TALL, Nred, nc);
-            dim3 grid((unsigned)((nobs + 31) / 32), (unsigned)((nc + 31) / 32)), block(32, 8);
-            scaled_transpose_kernel<<<grid, block, 0, ctx->stream>>>(S->d, S->ld, nobs, c0, nc, Rd.d(), Xt->d, Xt->ld);
+        scaled_outer_chunks(ctx, S, Rd.d(), [&](gsi_buf* O, int64_t c0, int64_t) {
+            tall_download(O, out_host + c0 * ldo, ldo, 0, Nred);
+        });
+    });
+}
+
+GSI_API int32_t gsi_pcga_direct_solve(gsi_ctx* ctx, int64_t nobs, int64_t K, const double* E, int64_t lde,
+                                      const double* HX, const double* Rdiag, const double* Rdense, int64_t ldr,
+                                      const double* b, double* x_out, int64_t* rank_out) {
+    return guarded([&] {
+        GSI_REQUIRE(ctx && b && x_out, GSI_ERR_INVALID_ARGUMENT, "null argument");
+        GSI_CUDA(cudaSetDevice(ctx->device));
+        GSI_REQUIRE(nobs >= 1 && nobs < 4096, GSI_ERR_UNSUPPORTED, "pcga direct solve: nobs must be in 1..4095");
+        PcgaDev dev(ctx, nobs, K, E, lde, HX, Rdiag, Rdense, ldr);     // validates and uploads E, HX, R
+        const int m = (int)nobs + 1;
+        const int64_t ldm = 2 * (int64_t)m;
+        DevMem M(ctx, (size_t)ldm * m * 8), bx(ctx, (size_t)2 * m * 8);
+        GSI_CUDA(cudaMemsetAsync(M.d(), 0, (size_t)ldm * m * 8, ctx->stream));
+        upload(ctx, bx.d(), b, m);
+        const dim3 blk(128), grd_all((unsigned)((nobs + 127) / 128));
+        auto place = [&](const gsi_buf* O, int64_t c0, int64_t nc) {
+            const dim3 grd(grd_all.x, (unsigned)nc);
+            saddle_block_kernel<<<grd, blk, 0, ctx->stream>>>(O ? O->d : nullptr, O ? O->ld : 0, (int)nobs, (int)c0,
+                                                              (int)nc, dev.op.Rdiag, dev.op.Rdense, M.d(), ldm);
             GSI_CUDA(cudaGetLastError());
             count_launch(ctx);
-            dense_apply(ctx, S, 0, Xt.get(), O.get(), 1.0);
-            tall_download(O.get(), out_host + c0 * ldo, ldo, 0, Nred);
+        };
+        if (K > 0) {
+            // HQH = sum_i eta_i eta_i' = E E'  (the reference's ger! loop, direct.jl:49-53) as one
+            // tensor-core product per 256-column chunk; E is zero-padded to >= 8 columns
+            const int64_t Kp = K < 8 ? 8 : K;
+            BufPtr Eb = make_buf(ctx, GSI_LAYOUT_COLMAJOR, nobs, Kp);
+            GSI_CUDA(cudaMemcpy2DAsync(Eb->d, Eb->ld * 8, dev.op.E, nobs * 8, nobs * 8, K, cudaMemcpyDeviceToDevice,
+                                       ctx->stream));
+            DevMem ones(ctx, (size_t)Kp * 8);
+            std::vector<double> one_h((size_t)Kp, 1.0);
+            upload(ctx, ones.d(), one_h.data(), Kp);
+            GSI_CUDA(cudaStreamSynchronize(ctx->stream));              // one_h leaves scope below
+            scaled_outer_chunks(ctx, Eb.get(), ones.d(), place);
+        } else {
+            for (int64_t c0 = 0; c0 < nobs; c0 += kMaxCols)
+                place(nullptr, c0, (nobs - c0 < kMaxCols) ? nobs - c0 : kMaxCols);
         }
+        saddle_border_kernel<<<(unsigned)((m + 127) / 128), 128, 0, ctx->stream>>>(dev.op.HX, (int)nobs, M.d(), ldm);
+        GSI_CUDA(cudaGetLastError());
+        count_launch(ctx);
+        jacobi_sweeps(ctx, M.d(), ldm, m, 2 * m, m);
+        const size_t smem = (size_t)(2 * m + LS_WARPS) * sizeof(double);
+        GSI_CUDA(cudaFuncSetAttribute(pinv_apply_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        int* drank = ctx->dflags + 2;
+        pinv_apply_kernel<<<1, LS_THREADS, smem, ctx->stream>>>(M.d(), ldm, m, bx.d(), bx.d() + m, drank);
+        GSI_CUDA(cudaGetLastError());
+        count_launch(ctx);
+        int hrank = 0;
+        GSI_CUDA(cudaMemcpyAsync(x_out, bx.d() + m, (size_t)m * 8, cudaMemcpyDeviceToHost, ctx->stream));
+        GSI_CUDA(cudaMemcpyAsync(&hrank, drank, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+        GSI_CUDA(cudaStreamSynchronize(ctx->stream));
+        if (rank_out) *rank_out = hrank;
     });
 }

@@ -22,8 +22,12 @@ __device__ __forceinline__ int rr_player(int i, int r, int np) {
     return i == 0 ? 0 : ((i - 1 + r) % (np - 1)) + 1;
 }
 
+// M: column-major, ncols columns of pitch ld.  The rotation angle of a column pair comes from
+// its first rows_dot rows; the rotation is applied to all rows_all >= rows_dot rows (rows below
+// rows_dot carry a matrix that accumulates the right singular vectors, e.g. an identity).
 __global__ void __launch_bounds__(JS_WARPS * 32)
-jacobi_round_kernel(double* __restrict__ M, int l, int np, int round, double tol, int* __restrict__ rotated) {
+jacobi_round_kernel(double* __restrict__ M, int64_t ld, int rows_dot, int rows_all, int l, int np, int round,
+                    double tol, int* __restrict__ rotated) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int t = blockIdx.x * JS_WARPS + warp;
     if (t >= np / 2) return;
@@ -31,10 +35,10 @@ jacobi_round_kernel(double* __restrict__ M, int l, int np, int round, double tol
     int q = rr_player(np - 1 - t, round, np);
     if (p >= l || q >= l) return;            // dummy player (odd l)
     if (p > q) { const int tmp = p; p = q; q = tmp; }
-    double* mp = M + (size_t)p * l;
-    double* mq = M + (size_t)q * l;
+    double* mp = M + (size_t)p * ld;
+    double* mq = M + (size_t)q * ld;
     double a = 0.0, b = 0.0, g = 0.0;
-    for (int i = lane; i < l; i += 32) {
+    for (int i = lane; i < rows_dot; i += 32) {
         const double x = mp[i], y = mq[i];
         a += x * x; b += y * y; g += x * y;
     }
@@ -45,7 +49,7 @@ jacobi_round_kernel(double* __restrict__ M, int l, int np, int round, double tol
     const double tt = (zeta >= 0.0 ? 1.0 : -1.0) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
     const double c = 1.0 / sqrt(1.0 + tt * tt);
     const double s = c * tt;
-    for (int i = lane; i < l; i += 32) {
+    for (int i = lane; i < rows_all; i += 32) {
         const double x = mp[i], y = mq[i];
         mp[i] = c * x - s * y;
         mq[i] = s * x + c * y;
@@ -78,20 +82,23 @@ __global__ void jacobi_finalize_kernel(const double* __restrict__ M, int l, doub
     }
 }
 
-// M: l x l column-major (ld = l), device.  U (l x l, ld = l) and sigma (l) device outputs.
-void svd_small(gsi_ctx* ctx, double* M, int l, double* U, double* sigma) {
-    GSI_REQUIRE(l >= 1 && l <= kMaxCols, GSI_ERR_UNSUPPORTED, "svd_small: l must be in 1..256");
-    const int np = (l + 1) / 2 * 2;
+// One-sided Jacobi sweeps (round-robin ordering, dgesvj tolerance sqrt(rows)*eps) until a whole
+// sweep rotates nothing: afterwards the first rows_dot rows of M hold U * diag(sigma) column by
+// column and rows [rows_dot, rows_all) hold the input rows there multiplied by the accumulated
+// rotations V.
+void jacobi_sweeps(gsi_ctx* ctx, double* M, int64_t ld, int rows_dot, int rows_all, int ncols) {
+    const int np = (ncols + 1) / 2 * 2;
     const int nrounds = np - 1;
     const int blocks = (np / 2 + JS_WARPS - 1) / JS_WARPS;
     int* rotated = ctx->dflags + 1;
-    const double tol = sqrt((double)l) * 2.220446049250313e-16;   // dgesvj's sqrt(m)*eps
+    const double tol = sqrt((double)rows_dot) * 2.220446049250313e-16;   // dgesvj's sqrt(m)*eps
     const int max_sweeps = 60;
-    bool converged = (l == 1);
+    bool converged = (ncols == 1);
     for (int sweep = 0; sweep < max_sweeps && !converged; ++sweep) {
         GSI_CUDA(cudaMemsetAsync(rotated, 0, sizeof(int), ctx->stream));
         for (int r = 0; r < nrounds; ++r) {
-            jacobi_round_kernel<<<blocks, JS_WARPS * 32, 0, ctx->stream>>>(M, l, np, r, tol, rotated);
+            jacobi_round_kernel<<<blocks, JS_WARPS * 32, 0, ctx->stream>>>(M, ld, rows_dot, rows_all, ncols, np, r, tol,
+                                                                           rotated);
         }
         GSI_CUDA(cudaGetLastError());
         count_launch(ctx, nrounds);
@@ -100,7 +107,13 @@ void svd_small(gsi_ctx* ctx, double* M, int l, double* U, double* sigma) {
         GSI_CUDA(cudaStreamSynchronize(ctx->stream));
         converged = (h == 0);
     }
-    GSI_REQUIRE(converged, GSI_ERR_NO_CONVERGENCE, "svd_small: Jacobi did not converge in 60 sweeps");
+    GSI_REQUIRE(converged, GSI_ERR_NO_CONVERGENCE, "Jacobi SVD did not converge in 60 sweeps");
+}
+
+// M: l x l column-major (ld = l), device.  U (l x l, ld = l) and sigma (l) device outputs.
+void svd_small(gsi_ctx* ctx, double* M, int l, double* U, double* sigma) {
+    GSI_REQUIRE(l >= 1 && l <= kMaxCols, GSI_ERR_UNSUPPORTED, "svd_small: l must be in 1..256");
+    jacobi_sweeps(ctx, M, l, l, l, l);
     jacobi_finalize_kernel<<<1, 1024, 0, ctx->stream>>>(M, l, U, sigma);
     GSI_CUDA(cudaGetLastError());
     count_launch(ctx);

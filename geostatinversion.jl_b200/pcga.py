@@ -158,6 +158,17 @@ class PCGALowRankMatrix:
             return x, dict(itn=itn.value, istop=istop.value)
         return x
 
+    def pinv_solve(self, b, return_rank=False):
+        """`pinv(bigA) * b` for the DENSE saddle-point matrix [HQH + R, HX; HX', 0] that
+        pcgadirect assembles (src/direct.jl:49-58), on the device (gsi_pcga_direct_solve)."""
+        b = np.ascontiguousarray(b, dtype=np.float64)
+        x = np.empty(self.nobs + 1)
+        rank = C.c_int64()
+        rd, rD, ldr = self._rargs()
+        check(self.ctx._lib.gsi_pcga_direct_solve(self.ctx._h, self.nobs, self.K, _pd(self.E), self.nobs,
+                                                  _pd(self.HX), rd, rD, ldr, _pd(b), _pd(x), C.byref(rank)))
+        return (x, rank.value) if return_rank else x
+
 
 # ---------------------------------------------------------------- forward models
 class LinearForwardModel:
@@ -275,8 +286,8 @@ def pcgalsqr(forwardmodel, s0, X, xis, R, y, maxiters=5, delta=SQRT_EPS, xtol=1e
 
 def pcgadirectiteration(forwardmodel, s, X, xis, R, y, delta, callback, ctx=None, pmap=map, _dev=None):
     """One direct PCGA iteration (reference src/direct.jl:37-67).  The (nobs+1)^2
-    saddle-point system is solved with the reference's `pinv` semantics on the host
-    (keyword-surface tier: SURVEY.md §8 a16 / f2)."""
+    saddle-point system is assembled and solved on the device with the reference's `pinv`
+    semantics (tensor-core E E', one-sided Jacobi SVD, Julia's rtol cut-off)."""
     ctx = ctx or default_context()
     Zk, K, tmp = _dev if _dev is not None else _xis_to_device(ctx, xis)
     try:
@@ -286,14 +297,8 @@ def pcgadirectiteration(forwardmodel, s, X, xis, R, y, delta, callback, ctx=None
         callback(s, results[K + 2])                             # direct.jl:47
 
         def solver(E, HX, R_, b):
-            nobs = E.shape[0]
-            rd, rD = _split_R(R_, nobs)
-            HQH = np.zeros((nobs, nobs))
-            for i in range(E.shape[1]):                         # ger!(1., etai, etai, HQH)  (:49-53)
-                HQH += np.outer(E[:, i], E[:, i])
-            Rm = np.diag(rd) if rd is not None else rD
-            bigA = np.block([[HQH + Rm, HX[:, None]], [HX[None, :], np.zeros((1, 1))]])   # :57
-            return np.linalg.pinv(bigA, rcond=np.finfo(np.float64).eps * min(bigA.shape)) @ b   # :58
+            # HQH = sum_i eta_i eta_i' (ger! loop, :49-53), bigA (:57), pinv(bigA) * b (:58)
+            return PCGALowRankMatrix(E, HX, R_, ctx).pinv_solve(b)
 
         return _finish_iteration(ctx, Zk, K, X, R, np.asarray(y, dtype=np.float64), results, delta, solver)
     finally:

@@ -205,6 +205,13 @@ int32_t gsi_pcga_lsqr_solve(gsi_ctx* ctx, int64_t nobs, int64_t K, const double*
                             const double* HX, const double* Rdiag, const double* Rdense,
                             int64_t ldr, const double* b, double atol, double btol, double conlim,
                             int64_t maxiter, double* x_out, int64_t* itn_out, int32_t* istop_out);
+/* x = pinv([HQH + R, HX; HX', 0]) * b with HQH = sum_i eta_i eta_i' (pcgadirect's dense solve,
+ * src/direct.jl:49-58), fully on device: HQH = E E' on the tensor-core GEMM, SVD by one-sided
+ * Jacobi, Julia's pinv cut-off (singular values <= eps * (nobs+1) * sigma_max are dropped).
+ * Arguments as in gsi_pcga_lsqr_solve; rank_out (optional) = number of singular values kept. */
+int32_t gsi_pcga_direct_solve(gsi_ctx* ctx, int64_t nobs, int64_t K, const double* E, int64_t lde,
+                              const double* HX, const double* Rdiag, const double* Rdense,
+                              int64_t ldr, const double* b, double* x_out, int64_t* rank_out);
 /* s = X*beta + sum_i xis[i] * dot(eta_i, xi_bar) (src/lsqr.jl:55-61).
  * Zk: TALL n x K (the xis as columns, device resident).  s_host: n.                   */
 int32_t gsi_pcga_update(gsi_ctx* ctx, const gsi_buf* Zk, int64_t K, const double* Xmean,

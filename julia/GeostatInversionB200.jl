@@ -4,7 +4,8 @@
 # transcription of the header (the same table the tested Python `ctypes` host uses,
 # geostatinversion.jl_b200/_lib.py).  It keeps the reference's call surface:
 #   RandMatFact.randsvd(A, K, p, q), rangefinder(A, l, q), getxis(Q, numxis, p, q, seed)
-# for A::Matrix{Float64}, A::KernelCovMatrix (new) and A::LowRankCovMatrix.
+# for A::Matrix{Float64}, A::KernelCovMatrix (new) and A::LowRankCovMatrix, and
+#   pcgalsqr / pcgadirect / pcga / rga with the reference's positional and keyword arguments.
 module GeostatInversionB200
 
 import Random
@@ -185,6 +186,132 @@ end
 function getxis(Q, numxis::Int, p::Int, q::Int=3, seed=nothing)
 	Z = randsvdwithseed(Q, numxis, p, q, seed)
 	return [Z[:, i] for i = 1:numxis]
+end
+
+# ---------------------------------------------------------------------------------------------
+# PCGA / RGA drivers behind the reference's keyword surface (src/lsqr.jl:20-63,
+# src/direct.jl:21-67, src/GeostatInversion.jl:101-105).  Transcription of the tested Python
+# host geostatinversion.jl_b200/pcga.py.  The user's forward model stays a Julia function run
+# under `pmap`, exactly as in the reference; the batch of K+3 parameter vectors, the
+# saddle-point solve and the update run on the device.
+import Distributed
+import SparseArrays
+
+splitR(R::Number, nobs) = (fill(Float64(R), nobs), nothing)
+splitR(R::AbstractVector, nobs) = (Vector{Float64}(R), nothing)
+splitR(R::LinearAlgebra.Diagonal, nobs) = (Vector{Float64}(R.diag), nothing)
+function splitR(R::SparseArrays.SparseMatrixCSC, nobs)
+	d = Vector{Float64}(LinearAlgebra.diag(R))
+	return SparseArrays.nnz(R - SparseArrays.spdiagm(0=>d)) == 0 ? (d, nothing) : (nothing, Matrix{Float64}(R))
+end
+splitR(R::AbstractMatrix, nobs) = (nothing, Matrix{Float64}(R))
+
+function xistodevice(ctx::Context, xis::Vector{Vector{Float64}})
+	Zk = reduce(hcat, xis)
+	return upload!(DeviceMatrix(ctx, GSI_LAYOUT_TALL, size(Zk)...), Zk)
+end
+
+"`paramstorun` batch (src/lsqr.jl:37-43 == src/direct.jl:39-45) as the columns of an n x (K+3) matrix"
+function paramstorun(ctx::Context, Zk::DeviceMatrix, K::Int, s::Vector{Float64}, X::Vector{Float64}, delta::Float64)
+	P = DeviceMatrix(ctx, GSI_LAYOUT_TALL, Zk.rows, K + 3)
+	GC.@preserve s X check(ccall((:gsi_pcga_paramstorun, LIB), Int32,
+		(Ptr{Cvoid}, Ptr{Cvoid}, Int64, Ptr{Float64}, Ptr{Float64}, Float64, Ptr{Cvoid}), ctx.h, Zk.h, K, s, X, delta, P.h))
+	return download(P)
+end
+
+# x = lsqr(PCGALowRankMatrix(etas, HX, R), b) (src/lsqr.jl:53-54) or pinv(bigA) * b (src/direct.jl:49-58)
+function saddlesolve(ctx::Context, E::Matrix{Float64}, HX::Vector{Float64}, R, b::Vector{Float64}, direct::Bool)
+	nobs, K = size(E)
+	rd, rD = splitR(R, nobs)
+	rdp = rd === nothing ? Ptr{Float64}(C_NULL) : pointer(rd)
+	rDp = rD === nothing ? Ptr{Float64}(C_NULL) : pointer(rD)
+	x = Vector{Float64}(undef, nobs + 1)
+	GC.@preserve E HX rd rD b x begin
+		if direct
+			check(ccall((:gsi_pcga_direct_solve, LIB), Int32,
+				(Ptr{Cvoid}, Int64, Int64, Ptr{Float64}, Int64, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Int64, Ptr{Float64}, Ptr{Float64}, Ptr{Int64}),
+				ctx.h, nobs, K, E, nobs, HX, rdp, rDp, nobs, b, x, C_NULL))
+		else
+			check(ccall((:gsi_pcga_lsqr_solve, LIB), Int32,
+				(Ptr{Cvoid}, Int64, Int64, Ptr{Float64}, Int64, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Int64, Ptr{Float64}, Float64, Float64, Float64, Int64, Ptr{Float64}, Ptr{Int64}, Ptr{Int32}),
+				ctx.h, nobs, K, E, nobs, HX, rdp, rDp, nobs, b, 0.0, 0.0, 0.0, 0, x, C_NULL, C_NULL))
+		end
+	end
+	return x
+end
+
+function pcgaiteration(forwardmodel::Function, s::Vector{Float64}, X::Vector{Float64}, Zk::DeviceMatrix, K::Int, R, y::Vector{Float64},
+		delta::Float64, callback::Function, direct::Bool, ctx::Context)
+	P = paramstorun(ctx, Zk, K, s, X, delta)
+	results = Distributed.pmap(forwardmodel, [P[:, i] for i = 1:K + 3])          # src/lsqr.jl:44
+	hs = results[K + 3]
+	callback(s, hs)                                                             # src/direct.jl:47
+	E = Matrix{Float64}(undef, length(hs), K)
+	for i = 1:K
+		E[:, i] = (results[i] - hs) / delta                                     # etas, :46-49
+	end
+	HX = (results[K + 1] - hs) / delta                                          # :50
+	Hs = (results[K + 2] - hs) / delta                                          # :51
+	b = [y - hs + Hs; 0.0]                                                      # :52
+	x = saddlesolve(ctx, E, HX, R, b, direct)
+	snew = Vector{Float64}(undef, Zk.rows)
+	GC.@preserve X E x snew check(ccall((:gsi_pcga_update, LIB), Int32,
+		(Ptr{Cvoid}, Ptr{Cvoid}, Int64, Ptr{Float64}, Ptr{Float64}, Int64, Int64, Ptr{Float64}, Ptr{Float64}),
+		ctx.h, Zk.h, K, X, E, size(E, 1), size(E, 1), x, snew))                 # s = X*beta + sum xi_i (eta_i . xi_bar), :55-61
+	return snew
+end
+
+function pcgaouter(forwardmodel, s0, X, xis, R, y, maxiters, delta, xtol, callback, direct, ctx)
+	Zk = xistodevice(ctx, xis)
+	K = length(xis)
+	converged = false
+	s = Vector{Float64}(s0)
+	itercount = 0
+	while !converged && itercount < maxiters                                    # src/lsqr.jl:24-31
+		olds = s
+		s = pcgaiteration(forwardmodel, s, Vector{Float64}(X), Zk, K, R, Vector{Float64}(y), Float64(delta), callback, direct, ctx)
+		if LinearAlgebra.norm(s - olds) < xtol
+			converged = true
+		end
+		itercount += 1
+	end
+	return s
+end
+
+"pcgalsqr(forwardmodel, s0, X, xis, R, y; maxiters=5, delta=sqrt(eps(Float64)), xtol=1e-6) -- src/lsqr.jl:20-33 (+ callback, SURVEY F5)"
+pcgalsqr(forwardmodel::Function, s0::Vector, X::Vector, xis::Array{Array{Float64, 1}, 1}, R, y::Vector;
+		maxiters::Int=5, delta::Float64=sqrt(eps(Float64)), xtol::Float64=1e-6, callback=(s, obs_cal)->nothing, ctx::Context=context()) =
+	pcgaouter(forwardmodel, s0, X, xis, R, y, maxiters, delta, xtol, callback, false, ctx)
+
+"pcgadirect(forwardmodel, s0, X, xis, R, y; maxiters=5, delta=sqrt(eps(Float64)), xtol=1e-6, callback=(s, obs_cal)->nothing) -- src/direct.jl:21-35"
+pcgadirect(forwardmodel::Function, s0::Vector, X::Vector, xis::Array{Array{Float64, 1}, 1}, R, y::Vector;
+		maxiters::Int=5, delta::Float64=sqrt(eps(Float64)), xtol::Float64=1e-6, callback=(s, obs_cal)->nothing, ctx::Context=context()) =
+	pcgaouter(forwardmodel, s0, X, xis, R, y, maxiters, delta, xtol, callback, true, ctx)
+
+const pcga = pcgadirect                                                         # src/GeostatInversion.jl:105
+
+"rga(forwardmodel, s0, X, xis, R, y, S; maxiters, delta, xtol, pcgafunc=pcgadirect, callback) -- src/GeostatInversion.jl:101-103"
+function rga(forwardmodel::Function, s0::Vector, X::Vector, xis::Array{Array{Float64, 1}, 1}, R, y::Vector, S::Matrix{Float64};
+		maxiters::Int=5, delta::Float64=sqrt(eps(Float64)), xtol::Float64=1e-6, pcgafunc=pcgadirect, callback=(s, obs_cal)->nothing,
+		ctx::Context=context())
+	Nred, nobs = size(S)
+	Sd = upload!(DeviceMatrix(ctx, GSI_LAYOUT_COLMAJOR, Nred, nobs), S)
+	function sketch(V::Matrix{Float64})                                         # S * V on the tensor-core GEMM
+		Vd = upload!(DeviceMatrix(ctx, GSI_LAYOUT_TALL, size(V)...), V)
+		out = DeviceMatrix(ctx, GSI_LAYOUT_TALL, Nred, size(V, 2))
+		check(ccall((:gsi_sketch_apply, LIB), Int32, (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}), ctx.h, Sd.h, Vd.h, out.h))
+		return download(out)
+	end
+	rd, rD = splitR(R, nobs)
+	if rd === nothing
+		SRS = sketch(rD * S')                                                   # dense R: S * (R * S')
+	else
+		SRS = Matrix{Float64}(undef, Nred, Nred)
+		GC.@preserve rd SRS check(ccall((:gsi_sketch_cov, LIB), Int32, (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Int64),
+			ctx.h, Sd.h, rd, SRS, Nred))
+	end
+	return pcgafunc(x->vec(sketch(reshape(forwardmodel(x), :, 1))), s0, X, xis, SRS, vec(sketch(reshape(Vector{Float64}(y), :, 1)));
+		maxiters=maxiters, delta=delta, xtol=xtol, callback=callback, ctx=ctx)
 end
 
 end

@@ -33,6 +33,7 @@ from .randmatfact import (colnorms, rangefinder_adaptive, rangefinder_fixed,
                           randsvd, eig_nystrom, lu_L_unpermuted)
 from .lowrank import LowRankCovMatrix, PCGALowRankMatrix
 from .lsqr import lsqr
-from .pcga import pcgalsqr, pcgalsqriteration, pcgadirect, pcgadirectiteration, rga, getxis
+from .pcga import (pcgalsqr, pcgalsqriteration, pcgadirect, pcgadirectiteration, pcgadirect_system, pinv, rga,
+                   getxis)
 from .kernels import kernel_cov_dense, scaled_coords, grid_coords
 from .metrics import singvals_from_Z, subspace_sine, compare_Z

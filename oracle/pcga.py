@@ -69,29 +69,42 @@ def pcgalsqr(forwardmodel, s0, X, xis, R, y, maxiters=5, delta=SQRT_EPS, xtol=1e
     return s
 
 
-def pcgadirectiteration(forwardmodel, s, X, xis, R, y, delta, callback):
-    """src/direct.jl:37-67."""
+def pcgadirect_system(forwardmodel, s, X, xis, R, y, delta, callback=lambda s, obs: None):
+    """src/direct.jl:39-57: the K+3 forward runs and the dense saddle-point system.
+    Returns (bigA, b, E) with E = [eta_1 .. eta_K] as columns."""
     K = len(xis)
     results = [np.asarray(forwardmodel(pv), dtype=np.float64) for pv in _paramstorun(s, X, xis, delta)]
     callback(s, results[K + 2])                            # :47
     hs = results[K + 2]
     nobs = len(y)
     HQH = np.zeros((nobs, nobs))                           # :49
+    E = np.empty((nobs, K))
     for i in range(K):                                     # :50-53
         etai = (results[i] - hs) / delta
+        E[:, i] = etai
         HQH += np.outer(etai, etai)
     HX = (results[K] - hs) / delta
     Hs = (results[K + 1] - hs) / delta
     b = np.concatenate([y - hs + Hs, np.zeros(1)])         # :56
     bigA = np.block([[_Radd(HQH, R), HX[:, None]], [HX[None, :], np.zeros((1, 1))]])  # :57
-    # Julia pinv default: rtol = eps * min(size) when atol == 0
-    x = np.linalg.pinv(bigA, rcond=np.finfo(np.float64).eps * min(bigA.shape)) @ b    # :58
+    return bigA, b, E
+
+
+def pinv(A):
+    """Julia `pinv(A)` with its defaults: atol = 0, rtol = eps * min(size(A)) (dgesdd SVD)."""
+    return np.linalg.pinv(A, rcond=np.finfo(np.float64).eps * min(A.shape))
+
+
+def pcgadirectiteration(forwardmodel, s, X, xis, R, y, delta, callback):
+    """src/direct.jl:37-67."""
+    K = len(xis)
+    bigA, b, E = pcgadirect_system(forwardmodel, s, X, xis, R, y, delta, callback)
+    x = pinv(bigA) @ b                                     # :58
     beta_bar = x[-1]
     xi_bar = x[:-1]
     snew = X * beta_bar
     for i in range(K):
-        etai = (results[i] - hs) / delta
-        snew = snew + xis[i] * np.dot(etai, xi_bar)
+        snew = snew + xis[i] * np.dot(E[:, i], xi_bar)
     return snew
 
 

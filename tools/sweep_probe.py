@@ -32,6 +32,10 @@ SCHEDULES = [
     (64, -4, 0, 4, 6),       # 4-tile separation
     (64, -1, 1, 8, 6),       # + evict_last hint
     (64, -1, 0, 64, 6),      # loose window (64 x 64 tiles = 240 MB: only stops runaway drift)
+    (64, -1, 0, 2, 4),       # tight: 2 x 16 tiles
+    (1, 0, 0, 16, 6),        # lock-step starts, wider window
+    (16, -1, 0, 8, 6),       # 16 start offsets
+    (64, 256, 0, 4, 6),      # quarter-of-X spread but bounded drift (each of the 64 groups stays L2-coherent)
 ]
 
 
