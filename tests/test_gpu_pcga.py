@@ -112,7 +112,7 @@ def test_device_lsqr_matches_oracle(gsi, nobs, K):
                                                   (64, 1, 1e-3, False), (513, 8, 1e-4, False)])
 def test_device_direct_solve_matches_oracle(gsi, nobs, K, noise, dense_R):
     """`pinv([HQH + R, HX; HX', 0]) * b` (src/direct.jl:49-58) on the device vs the oracle's
-    dgesdd pinv with Julia's cut-off.  Tolerance 20 * eps * cond (two SVD algorithms on one
+    dgesdd pinv with Julia's cut-off.  Tolerance 10 * eps * cond (two SVD algorithms on one
     ill-conditioned matrix); the retained rank must be identical."""
     rng = np.random.default_rng(nobs * 7 + K)
     etas = [rng.standard_normal(nobs) for _ in range(K)]
@@ -129,7 +129,7 @@ def test_device_direct_solve_matches_oracle(gsi, nobs, K, noise, dense_R):
     x, rank = gsi.PCGALowRankMatrix(etas, HX, R).pinv_solve(b, return_rank=True)
     assert rank == int(np.sum(sv > cut)) == nobs + 1
     cond = sv[0] / sv[-1]
-    assert relerr(x, oracle.pinv(big) @ b) < 20 * np.finfo(float).eps * cond
+    assert relerr(x, oracle.pinv(big) @ b) < 10 * np.finfo(float).eps * cond
     assert relerr(big @ x, b) < 20 * np.finfo(float).eps * cond
 
 
@@ -175,7 +175,7 @@ def test_simpletestpcga(gsi, log2N, log2M, mu):
     forward model.
 
     Parity bar: ONE iteration from identical s (identical forward-model evaluations) agrees
-    to 1e-8 with a converged LSQR, and to 20 * eps * cond(bigA) for the direct solve: the
+    to 1e-8 with a converged LSQR, and to 10 * eps * cond(bigA) for the direct solve: the
     reference applies `pinv` (dgesdd) to a saddle-point matrix of condition 1e9..1e11
     (R = 1e-8), and two backward-stable SVDs -- the device's one-sided Jacobi, or just
     LAPACK's dgesvd instead of dgesdd -- differ by that much on it (measured: Jacobi and dgesvd
@@ -194,7 +194,7 @@ def test_simpletestpcga(gsi, log2N, log2M, mu):
     bigA = oracle.pcgadirect_system(forward, p0, X, xis, R, yobs, delta)[0]
     sv = np.linalg.svd(bigA, compute_uv=False)
     sv = sv[sv > np.finfo(float).eps * len(sv) * sv[0]]
-    assert relerr(s1, s1o) < max(1e-8, 20 * np.finfo(float).eps * sv[0] / sv[-1])
+    assert relerr(s1, s1o) < max(1e-8, 10 * np.finfo(float).eps * sv[0] / sv[-1])
     popt = gsi.pcgadirect(forward, p0, X, xis, R, yobs)
     assert np.linalg.norm(popt - truep) / np.linalg.norm(truep) < 2e-2
     assert relerr(popt, oracle.pcgadirect(forward, p0, X, xis, R, yobs)) < 1e-3
