@@ -129,6 +129,8 @@ GSI_API int32_t gsi_ctx_create(int32_t device, int32_t rank, int32_t world, cons
         GSI_CUDA(cudaMalloc(&ctx->scratch, ctx->scratch_doubles * sizeof(double)));
         GSI_CUDA(cudaMalloc(&ctx->dflags, 16 * sizeof(int)));
         GSI_CUDA(cudaMemset(ctx->dflags, 0, 16 * sizeof(int)));
+        GSI_CUDA(cudaMalloc(&ctx->jflags, 64 * sizeof(int)));
+        if (const char* e = getenv("GSI_SVD_FUSED")) ctx->svd_fused = atoi(e) != 0;
         GSI_CUDA(cudaEventCreate(&ctx->ev0));
         GSI_CUDA(cudaEventCreate(&ctx->ev1));
         if (const char* e = getenv("GSI_SWEEP"))      // "groups,div,hint[,window[,epoch_shift]]": see gsi_ctx_set_option
@@ -148,6 +150,7 @@ static void ctx_really_destroy(gsi_ctx* ctx) {
     if (ctx->scratch) cudaFree(ctx->scratch);
     if (ctx->dflags) cudaFree(ctx->dflags);
     if (ctx->sweep_cnt) cudaFree(ctx->sweep_cnt);
+    if (ctx->jflags) cudaFree(ctx->jflags);
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
     for (cudaEvent_t e : ctx->ev_pool) cudaEventDestroy(e);
@@ -198,6 +201,7 @@ GSI_API int32_t gsi_ctx_set_option(gsi_ctx* ctx, const char* name, int64_t value
         else if (n == "kcov.l2_hint") ctx->kcov_l2_hint = v;
         else if (n == "kcov.window") ctx->kcov_window = v;
         else if (n == "kcov.epoch_shift") ctx->kcov_epoch_shift = v;
+        else if (n == "svd.fused") ctx->svd_fused = v != 0;
         else throw Error(GSI_ERR_INVALID_ARGUMENT, "unknown option '" + n + "'");
         try {
             validate_kcov_options(ctx);
@@ -219,6 +223,7 @@ GSI_API int32_t gsi_ctx_get_option(gsi_ctx* ctx, const char* name, int64_t* valu
         else if (n == "kcov.l2_hint") *value_out = ctx->kcov_l2_hint;
         else if (n == "kcov.window") *value_out = ctx->kcov_window;
         else if (n == "kcov.epoch_shift") *value_out = ctx->kcov_epoch_shift;
+        else if (n == "svd.fused") *value_out = ctx->svd_fused;
         else throw Error(GSI_ERR_INVALID_ARGUMENT, "unknown option '" + n + "'");
     });
 }

@@ -89,6 +89,9 @@ struct gsi_ctx {
     int kcov_epoch_shift = 6;            // epoch = 2^shift k-tiles
     unsigned int* sweep_cnt = nullptr;   // per-epoch arrival counters of one launch
     size_t sweep_cnt_n = 0;
+    // small Jacobi SVD: all sweeps in one cluster launch (svd.cu; gsi_ctx_set_option "svd.fused")
+    int svd_fused = 0;
+    int* jflags = nullptr;               // [60] rotations per sweep, [60] sweeps used
 };
 
 struct gsi_buf {

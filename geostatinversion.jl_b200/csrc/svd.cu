@@ -5,11 +5,24 @@
 // launches on the stream (the matrix, <= 512 KB, stays in L2).  Columns of M converge
 // to U * diag(sigma); they are normalised and sorted (descending, LAPACK order) at the
 // end.  High relative accuracy is the reason for Jacobi over bidiagonalisation.
+//
+// Two drivers of the same rotation sequence (bit-identical results):
+//   * jacobi_round_kernel: one launch per round (any size);
+//   * jacobi_fused_kernel: ALL sweeps in one launch of a single thread-block cluster (up to
+//     8 CTAs x 32 warps = 256 column pairs, i.e. <= 512 columns), rounds separated by the
+//     hardware cluster barrier instead of a kernel boundary, convergence decided on the device.
+//     A round is ~2 L2 round trips of work, so the ~3 us fixed cost of a launch dominated the
+//     per-round version (1881 launches, 10.7 ms at l = 210).  Option "svd.fused".
 #include "common.cuh"
+#include <cooperative_groups.h>
+
+namespace cg = cooperative_groups;
 
 namespace gsi {
 
 constexpr int JS_WARPS = 8;
+constexpr int JF_MAX_CTAS = 8;       // portable cluster size
+constexpr int JF_MAX_SWEEPS = 60;
 
 __device__ __forceinline__ double warp_sum(double v) {
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
@@ -56,6 +69,86 @@ jacobi_round_kernel(double* __restrict__ M, int64_t ld, int rows_dot, int rows_a
     }
 }
 
+// All sweeps in one launch: grid = ONE cluster; pair slot t = cluster-wide warp index.  Matrix
+// data moves through L2 (ld.cg / st.cg) and rounds are separated by cluster.sync() (release /
+// acquire at cluster scope), so a column written in round r by one CTA is read in round r+1 by
+// another.  rotated[sweep] counts the rotations of a sweep; every thread reads it after the
+// sweep's last barrier, so the exit decision is uniform.  The arithmetic and its order per pair
+// are those of jacobi_round_kernel.  NR > 0: rows_all <= 32*NR and the two columns stay in
+// registers between the dot products and the rotation (then ncols <= 256, i.e. <= 128 pairs and
+// at most 16 warps per CTA, which leaves 128 registers per thread).
+template <int NR>
+__global__ void __launch_bounds__(NR > 0 ? 512 : 1024)
+jacobi_fused_kernel(double* __restrict__ M, int64_t ld, int rows_dot, int rows_all, int l, int np, double tol,
+                    int* __restrict__ rotated, int* __restrict__ sweeps_out) {
+    cg::cluster_group cluster = cg::this_cluster();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int t = (int)cluster.block_rank() * (int)(blockDim.x >> 5) + warp;
+    int done = -1;
+    for (int sweep = 0; sweep < JF_MAX_SWEEPS; ++sweep) {
+        for (int round = 0; round < np - 1; ++round) {
+            int p = 0, q = 0;
+            bool live = t < np / 2;
+            if (live) {
+                p = rr_player(t, round, np);
+                q = rr_player(np - 1 - t, round, np);
+                live = p < l && q < l;                       // dummy player (odd l)
+            }
+            if (live) {
+                if (p > q) { const int tmp = p; p = q; q = tmp; }
+                double* mp = M + (size_t)p * ld;
+                double* mq = M + (size_t)q * ld;
+                double a = 0.0, b = 0.0, g = 0.0;
+                double xr[NR > 0 ? NR : 1], yr[NR > 0 ? NR : 1];
+                if (NR > 0) {
+#pragma unroll
+                    for (int k = 0; k < NR; ++k) {
+                        const int i = lane + 32 * k;
+                        xr[k] = i < rows_all ? __ldcg(mp + i) : 0.0;
+                        yr[k] = i < rows_all ? __ldcg(mq + i) : 0.0;
+                    }
+#pragma unroll
+                    for (int k = 0; k < NR; ++k) {
+                        if (lane + 32 * k < rows_dot) { a += xr[k] * xr[k]; b += yr[k] * yr[k]; g += xr[k] * yr[k]; }
+                    }
+                } else {
+                    for (int i = lane; i < rows_dot; i += 32) {
+                        const double x = __ldcg(mp + i), y = __ldcg(mq + i);
+                        a += x * x; b += y * y; g += x * y;
+                    }
+                }
+                a = warp_sum(a); b = warp_sum(b); g = warp_sum(g);
+                if (!(fabs(g) <= tol * sqrt(a * b) || g == 0.0)) {
+                    if (lane == 0) atomicAdd(rotated + sweep, 1);
+                    const double zeta = (b - a) / (2.0 * g);
+                    const double tt = (zeta >= 0.0 ? 1.0 : -1.0) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
+                    const double c = 1.0 / sqrt(1.0 + tt * tt);
+                    const double s = c * tt;
+                    if (NR > 0) {
+#pragma unroll
+                        for (int k = 0; k < NR; ++k) {
+                            const int i = lane + 32 * k;
+                            if (i < rows_all) {
+                                __stcg(mp + i, c * xr[k] - s * yr[k]);
+                                __stcg(mq + i, s * xr[k] + c * yr[k]);
+                            }
+                        }
+                    } else {
+                        for (int i = lane; i < rows_all; i += 32) {
+                            const double x = __ldcg(mp + i), y = __ldcg(mq + i);
+                            __stcg(mp + i, c * x - s * y);
+                            __stcg(mq + i, s * x + c * y);
+                        }
+                    }
+                }
+            }
+            cluster.sync();
+        }
+        if (__ldcg(rotated + sweep) == 0) { done = sweep + 1; break; }
+    }
+    if (t == 0 && lane == 0) *sweeps_out = done;
+}
+
 // sigma_j = ||m_j||, rank by descending sigma (ties: lower index first), write normalised
 // columns to U in sorted order.
 __global__ void jacobi_finalize_kernel(const double* __restrict__ M, int l, double* __restrict__ U,
@@ -86,8 +179,49 @@ __global__ void jacobi_finalize_kernel(const double* __restrict__ M, int l, doub
 // sweep rotates nothing: afterwards the first rows_dot rows of M hold U * diag(sigma) column by
 // column and rows [rows_dot, rows_all) hold the input rows there multiplied by the accumulated
 // rotations V.
+template <int NR>
+static void launch_jacobi_fused(gsi_ctx* ctx, int nctas, int wpc, double* M, int64_t ld, int rows_dot, int rows_all,
+                                int ncols, int np, double tol) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)nctas);
+    cfg.blockDim = dim3((unsigned)wpc * 32);
+    cfg.dynamicSmemBytes = 0;
+    cfg.stream = ctx->stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = (unsigned)nctas;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    GSI_CUDA(cudaLaunchKernelEx(&cfg, jacobi_fused_kernel<NR>, M, ld, rows_dot, rows_all, ncols, np, tol, ctx->jflags,
+                                ctx->jflags + JF_MAX_SWEEPS));
+}
+
+// Single-launch driver; returns false when the problem does not fit one cluster.
+static bool jacobi_sweeps_fused(gsi_ctx* ctx, double* M, int64_t ld, int rows_dot, int rows_all, int ncols, int np,
+                                double tol) {
+    const int pairs = np / 2;
+    if (pairs > JF_MAX_CTAS * 32 || ncols < 2) return false;
+    int nctas = pairs < JF_MAX_CTAS ? pairs : JF_MAX_CTAS;
+    const int wpc = (pairs + nctas - 1) / nctas;
+    GSI_CUDA(cudaMemsetAsync(ctx->jflags, 0, (JF_MAX_SWEEPS + 1) * sizeof(int), ctx->stream));
+    if (rows_all <= 128 && wpc <= 16) launch_jacobi_fused<4>(ctx, nctas, wpc, M, ld, rows_dot, rows_all, ncols, np, tol);
+    else if (rows_all <= 256 && wpc <= 16) launch_jacobi_fused<8>(ctx, nctas, wpc, M, ld, rows_dot, rows_all, ncols, np, tol);
+    else launch_jacobi_fused<0>(ctx, nctas, wpc, M, ld, rows_dot, rows_all, ncols, np, tol);
+    count_launch(ctx);
+    int h = 0;
+    GSI_CUDA(cudaMemcpyAsync(&h, ctx->jflags + JF_MAX_SWEEPS, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    GSI_CUDA(cudaStreamSynchronize(ctx->stream));
+    GSI_REQUIRE(h > 0, GSI_ERR_NO_CONVERGENCE, "Jacobi SVD did not converge in 60 sweeps");
+    return true;
+}
+
 void jacobi_sweeps(gsi_ctx* ctx, double* M, int64_t ld, int rows_dot, int rows_all, int ncols) {
     const int np = (ncols + 1) / 2 * 2;
+    if (ctx->svd_fused &&
+        jacobi_sweeps_fused(ctx, M, ld, rows_dot, rows_all, ncols, np, sqrt((double)rows_dot) * 2.220446049250313e-16))
+        return;
     const int nrounds = np - 1;
     const int blocks = (np / 2 + JS_WARPS - 1) / JS_WARPS;
     int* rotated = ctx->dflags + 1;

@@ -150,6 +150,44 @@ def test_svd_small(gsi, l):
     assert np.max(np.abs(np.linalg.norm(U.T @ M, axis=1) - s) / sref[0]) < 1e-13
 
 
+@pytest.mark.parametrize("l", [2, 3, 60, 129, 210, 256])
+def test_svd_small_fused_matches_per_round(gsi, l):
+    """The single-launch cluster driver of the Jacobi SVD ("svd.fused") performs the same
+    rotations in the same order as the launch-per-round driver: bit-identical U and sigma."""
+    ctx = gsi.default_context()
+    rng = np.random.default_rng(1000 + l)
+    M = np.triu(rng.standard_normal((l, l))) * (10.0 ** (-6 * np.arange(l) / max(l - 1, 1)))[:, None]
+    saved = ctx.get_option("svd.fused")
+    try:
+        ctx.set_option("svd.fused", 0)
+        U0, s0 = gsi.svd_small(M)
+        ctx.set_option("svd.fused", 1)
+        U1, s1 = gsi.svd_small(M)
+    finally:
+        ctx.set_option("svd.fused", saved)
+    assert np.array_equal(s0, s1) and np.array_equal(U0, U1)
+
+
+@pytest.mark.parametrize("nobs", [7, 64, 200, 513])
+def test_direct_solve_fused_matches_per_round(gsi, nobs):
+    """Same for the pinv solve of pcgadirect (Jacobi with accumulated V, rectangular 2m x m):
+    register-resident columns (2m <= 256), streamed columns, and the fall-back above 512 columns."""
+    ctx = gsi.default_context()
+    rng = np.random.default_rng(nobs)
+    etas = [rng.standard_normal(nobs) for _ in range(5)]
+    A = gsi.PCGALowRankMatrix(etas, rng.standard_normal(nobs), 1e-4 * (1 + rng.random(nobs)))
+    b = np.concatenate([rng.standard_normal(nobs), [0.0]])
+    saved = ctx.get_option("svd.fused")
+    try:
+        ctx.set_option("svd.fused", 0)
+        x0 = A.pinv_solve(b)
+        ctx.set_option("svd.fused", 1)
+        x1 = A.pinv_solve(b)
+    finally:
+        ctx.set_option("svd.fused", saved)
+    assert np.array_equal(x0, x1)
+
+
 def test_lowrankcov_algebra(gsi):
     """testrpcga.jl:46-58 on the device operator."""
     samples = [np.array([-.5, 0., .5]), np.array([1., -1., 0.]), np.array([-.5, 1., -.5])]
