@@ -35,6 +35,24 @@ __device__ __forceinline__ int rr_player(int i, int r, int np) {
     return i == 0 ? 0 : ((i - 1 + r) % (np - 1)) + 1;
 }
 
+// The arithmetic of one pair, with every multiply-add spelled out so that both drivers round
+// identically whatever the compiler would otherwise contract.
+__device__ __forceinline__ void jacobi_acc(double x, double y, double& a, double& b, double& g) {
+    a = fma(x, x, a); b = fma(y, y, b); g = fma(x, y, g);
+}
+__device__ __forceinline__ bool jacobi_angle(double a, double b, double g, double tol, double& c, double& s) {
+    if (fabs(g) <= tol * sqrt(__dmul_rn(a, b)) || g == 0.0) return false;
+    const double zeta = (b - a) / (2.0 * g);
+    const double tt = (zeta >= 0.0 ? 1.0 : -1.0) / (fabs(zeta) + sqrt(fma(zeta, zeta, 1.0)));
+    c = 1.0 / sqrt(fma(tt, tt, 1.0));
+    s = __dmul_rn(c, tt);
+    return true;
+}
+__device__ __forceinline__ void jacobi_rot(double c, double s, double x, double y, double& nx, double& ny) {
+    nx = fma(c, x, -__dmul_rn(s, y));
+    ny = fma(s, x, __dmul_rn(c, y));
+}
+
 // M: column-major, ncols columns of pitch ld.  The rotation angle of a column pair comes from
 // its first rows_dot rows; the rotation is applied to all rows_all >= rows_dot rows (rows below
 // rows_dot carry a matrix that accumulates the right singular vectors, e.g. an identity).
@@ -51,21 +69,16 @@ jacobi_round_kernel(double* __restrict__ M, int64_t ld, int rows_dot, int rows_a
     double* mp = M + (size_t)p * ld;
     double* mq = M + (size_t)q * ld;
     double a = 0.0, b = 0.0, g = 0.0;
-    for (int i = lane; i < rows_dot; i += 32) {
-        const double x = mp[i], y = mq[i];
-        a += x * x; b += y * y; g += x * y;
-    }
+    for (int i = lane; i < rows_dot; i += 32) jacobi_acc(mp[i], mq[i], a, b, g);
     a = warp_sum(a); b = warp_sum(b); g = warp_sum(g);
-    if (fabs(g) <= tol * sqrt(a * b) || g == 0.0) return;
+    double c, s;
+    if (!jacobi_angle(a, b, g, tol, c, s)) return;
     if (lane == 0) atomicAdd(rotated, 1);
-    const double zeta = (b - a) / (2.0 * g);
-    const double tt = (zeta >= 0.0 ? 1.0 : -1.0) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
-    const double c = 1.0 / sqrt(1.0 + tt * tt);
-    const double s = c * tt;
     for (int i = lane; i < rows_all; i += 32) {
-        const double x = mp[i], y = mq[i];
-        mp[i] = c * x - s * y;
-        mq[i] = s * x + c * y;
+        double nx, ny;
+        jacobi_rot(c, s, mp[i], mq[i], nx, ny);
+        mp[i] = nx;
+        mq[i] = ny;
     }
 }
 
@@ -109,35 +122,32 @@ jacobi_fused_kernel(double* __restrict__ M, int64_t ld, int rows_dot, int rows_a
                     }
 #pragma unroll
                     for (int k = 0; k < NR; ++k) {
-                        if (lane + 32 * k < rows_dot) { a += xr[k] * xr[k]; b += yr[k] * yr[k]; g += xr[k] * yr[k]; }
+                        if (lane + 32 * k < rows_dot) jacobi_acc(xr[k], yr[k], a, b, g);
                     }
                 } else {
-                    for (int i = lane; i < rows_dot; i += 32) {
-                        const double x = __ldcg(mp + i), y = __ldcg(mq + i);
-                        a += x * x; b += y * y; g += x * y;
-                    }
+                    for (int i = lane; i < rows_dot; i += 32) jacobi_acc(__ldcg(mp + i), __ldcg(mq + i), a, b, g);
                 }
                 a = warp_sum(a); b = warp_sum(b); g = warp_sum(g);
-                if (!(fabs(g) <= tol * sqrt(a * b) || g == 0.0)) {
+                double c, s;
+                if (jacobi_angle(a, b, g, tol, c, s)) {
                     if (lane == 0) atomicAdd(rotated + sweep, 1);
-                    const double zeta = (b - a) / (2.0 * g);
-                    const double tt = (zeta >= 0.0 ? 1.0 : -1.0) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
-                    const double c = 1.0 / sqrt(1.0 + tt * tt);
-                    const double s = c * tt;
                     if (NR > 0) {
 #pragma unroll
                         for (int k = 0; k < NR; ++k) {
                             const int i = lane + 32 * k;
                             if (i < rows_all) {
-                                __stcg(mp + i, c * xr[k] - s * yr[k]);
-                                __stcg(mq + i, s * xr[k] + c * yr[k]);
+                                double nx, ny;
+                                jacobi_rot(c, s, xr[k], yr[k], nx, ny);
+                                __stcg(mp + i, nx);
+                                __stcg(mq + i, ny);
                             }
                         }
                     } else {
                         for (int i = lane; i < rows_all; i += 32) {
-                            const double x = __ldcg(mp + i), y = __ldcg(mq + i);
-                            __stcg(mp + i, c * x - s * y);
-                            __stcg(mq + i, s * x + c * y);
+                            double nx, ny;
+                            jacobi_rot(c, s, __ldcg(mp + i), __ldcg(mq + i), nx, ny);
+                            __stcg(mp + i, nx);
+                            __stcg(mq + i, ny);
                         }
                     }
                 }
