@@ -273,14 +273,18 @@ def main():
         e2e = {"value": F / (e2e_ms * 1e-3) * 1e-12, "unit": "TFLOP/s", "ms_per_step": e2e_ms,
                "h2d_bytes_per_step": int(world * n * l * 8), "d2h_bytes_per_step": int(n * l * 8)}
 
+    # k-sweep schedule of the product kernel (gsi_ctx_set_option / GSI_SWEEP): groups,div,hint,window,epoch_shift
+    schedule = ",".join(str(ctx.get_option(k)) for k in ("kcov.sweep_groups", "kcov.sweep_div", "kcov.l2_hint",
+                                                         "kcov.window", "kcov.epoch_shift"))
     if rank == 0:
         gemm_ms, gemm_launches, gemm_flops = gemm
         traffic = None
         try:
             with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
                 tj = json.load(f)
-            if world == 1 and args.generation == "table" and args.workload in tj:
-                traffic = tj[args.workload]["bytes_per_launch"]      # from the committed ncu capture
+            if (world == 1 and args.generation == "table" and args.workload in tj
+                    and tj[args.workload].get("schedule") == schedule):
+                traffic = tj[args.workload]["bytes_per_launch"]      # from the committed ncu capture of this schedule
         except Exception:
             traffic = None
         ach = gemm_flops / (gemm_ms * 1e-3) * 1e-12 if gemm_ms > 0 else None
@@ -299,7 +303,8 @@ def main():
                           "normaliser": "LU_REF", "parallelism": f"row-shard x{world}",
                           "kernel_values": ("lattice table look-up (structured grid, n distinct values)"
                                             if args.generation == "table" else "exp/sqrt arithmetic from coordinates"),
-                          "l2": "operand streams (X 366 MB/pass) exceed L2; no flush needed"},
+                          "l2": "operand streams (X 366 MB/pass) exceed L2; no flush needed",
+                          "kcov_schedule": schedule, "svd_fused": ctx.get_option("svd.fused")},
                "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roof,
                "phase_ms_per_step": {k: v / args.steps for k, v in phases.items()}}
         if not args.no_cpu_baseline and world == 1:
