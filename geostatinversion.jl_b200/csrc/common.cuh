@@ -90,7 +90,7 @@ struct gsi_ctx {
     unsigned int* sweep_cnt = nullptr;   // per-epoch arrival counters of one launch
     size_t sweep_cnt_n = 0;
     // small Jacobi SVD: all sweeps in one cluster launch (svd.cu; gsi_ctx_set_option "svd.fused")
-    int svd_fused = 0;
+    int svd_fused = 1;
     int* jflags = nullptr;               // [60] rotations per sweep, [60] sweeps used
 };
 

@@ -190,7 +190,7 @@ __global__ void jacobi_finalize_kernel(const double* __restrict__ M, int l, doub
 // column and rows [rows_dot, rows_all) hold the input rows there multiplied by the accumulated
 // rotations V.
 template <int NR>
-static void launch_jacobi_fused(gsi_ctx* ctx, int nctas, int wpc, double* M, int64_t ld, int rows_dot, int rows_all,
+static cudaError_t launch_jacobi_fused(gsi_ctx* ctx, int nctas, int wpc, double* M, int64_t ld, int rows_dot, int rows_all,
                                 int ncols, int np, double tol) {
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)nctas);
@@ -204,8 +204,8 @@ static void launch_jacobi_fused(gsi_ctx* ctx, int nctas, int wpc, double* M, int
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    GSI_CUDA(cudaLaunchKernelEx(&cfg, jacobi_fused_kernel<NR>, M, ld, rows_dot, rows_all, ncols, np, tol, ctx->jflags,
-                                ctx->jflags + JF_MAX_SWEEPS));
+    return cudaLaunchKernelEx(&cfg, jacobi_fused_kernel<NR>, M, ld, rows_dot, rows_all, ncols, np, tol, ctx->jflags,
+                              ctx->jflags + JF_MAX_SWEEPS);
 }
 
 // Single-launch driver; returns false when the problem does not fit one cluster.
@@ -216,9 +216,16 @@ static bool jacobi_sweeps_fused(gsi_ctx* ctx, double* M, int64_t ld, int rows_do
     int nctas = pairs < JF_MAX_CTAS ? pairs : JF_MAX_CTAS;
     const int wpc = (pairs + nctas - 1) / nctas;
     GSI_CUDA(cudaMemsetAsync(ctx->jflags, 0, (JF_MAX_SWEEPS + 1) * sizeof(int), ctx->stream));
-    if (rows_all <= 128 && wpc <= 16) launch_jacobi_fused<4>(ctx, nctas, wpc, M, ld, rows_dot, rows_all, ncols, np, tol);
-    else if (rows_all <= 256 && wpc <= 16) launch_jacobi_fused<8>(ctx, nctas, wpc, M, ld, rows_dot, rows_all, ncols, np, tol);
-    else launch_jacobi_fused<0>(ctx, nctas, wpc, M, ld, rows_dot, rows_all, ncols, np, tol);
+    cudaError_t e;
+    if (rows_all <= 128 && wpc <= 16) e = launch_jacobi_fused<4>(ctx, nctas, wpc, M, ld, rows_dot, rows_all, ncols, np, tol);
+    else if (rows_all <= 256 && wpc <= 16) e = launch_jacobi_fused<8>(ctx, nctas, wpc, M, ld, rows_dot, rows_all, ncols, np, tol);
+    else e = launch_jacobi_fused<0>(ctx, nctas, wpc, M, ld, rows_dot, rows_all, ncols, np, tol);
+    if (e != cudaSuccess) {
+        // the cluster could not be scheduled on this device / partition: use the per-round driver from now on
+        cudaGetLastError();
+        ctx->svd_fused = 0;
+        return false;
+    }
     count_launch(ctx);
     int h = 0;
     GSI_CUDA(cudaMemcpyAsync(&h, ctx->jflags + JF_MAX_SWEEPS, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));

@@ -109,8 +109,8 @@ int32_t gsi_ctx_phase_timing(gsi_ctx* ctx, double* ms_out8, int32_t reset);
  *   "kcov.window"        > 0: a CTA runs at most this many epochs ahead of the slowest CTA,
  *                        which keeps the shared X stream L2-resident; 0: unthrottled
  *   "kcov.epoch_shift"   epoch = 2^shift k-tiles of 32 points
- *   "svd.fused"          1: the small Jacobi SVD (<= 512 columns) runs all sweeps in one
- *                        thread-block-cluster launch; 0: one launch per round (same rotations)
+ *   "svd.fused"          1 (default): the small Jacobi SVD (<= 512 columns) runs all sweeps in
+ *                        one thread-block-cluster launch; 0: one launch per round (same rotations)
  * The environment variable GSI_SWEEP="groups,div,hint[,window[,epoch_shift]]" sets the
  * same knobs at context creation.                                                     */
 int32_t gsi_ctx_set_option(gsi_ctx* ctx, const char* name, int64_t value);

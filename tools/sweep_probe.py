@@ -23,20 +23,38 @@ sys.path.insert(0, ROOT)
 from bench import WORKLOADS  # noqa: E402
 
 # (sweep_groups, sweep_div, l2_hint, window, epoch_shift)
-SCHEDULES = [
-    (64, 256, 0, 0, 6),      # round-1 default: de-synchronised over a quarter of X, unthrottled
-    (64, -1, 0, 4, 6),       # 1-tile separation, window of 4 x 64 tiles
-    (64, -1, 0, 16, 6),
-    (64, -1, 0, 2, 5),
-    (1, 0, 0, 4, 6),         # lock-step starts
-    (64, -4, 0, 4, 6),       # 4-tile separation
-    (64, -1, 1, 8, 6),       # + evict_last hint
-    (64, -1, 0, 64, 6),      # loose window (64 x 64 tiles = 240 MB: only stops runaway drift)
-    (64, -1, 0, 2, 4),       # tight: 2 x 16 tiles
-    (1, 0, 0, 16, 6),        # lock-step starts, wider window
-    (16, -1, 0, 8, 6),       # 16 start offsets
-    (64, 256, 0, 4, 6),      # quarter-of-X spread but bounded drift (each of the 64 groups stays L2-coherent)
-]
+SCHEDULE_SETS = {
+    # first pass (profiles/r01/sweep_schedules_c3_summary.csv): ONE coherent front (all CTAs within a few
+    # MB of X) cuts DRAM traffic 611 -> 8 GB per launch but runs 13 % slower, whatever the window
+    "coherent": [
+        (64, 256, 0, 0, 6),      # round-1 default: de-synchronised over a quarter of X, unthrottled
+        (64, -1, 0, 4, 6),       # 1-tile separation, window of 4 x 64 tiles
+        (64, -1, 0, 16, 6),
+        (64, -1, 0, 2, 5),
+        (1, 0, 0, 4, 6),         # lock-step starts
+        (64, -4, 0, 4, 6),       # 4-tile separation
+        (64, -1, 1, 8, 6),       # + evict_last hint
+        (64, -1, 0, 64, 6),      # loose window (64 x 64 tiles = 240 MB: only stops runaway drift)
+        (64, -1, 0, 2, 4),       # tight: 2 x 16 tiles
+        (1, 0, 0, 16, 6),        # lock-step starts, wider window
+        (16, -1, 0, 8, 6),       # 16 start offsets
+        (64, 256, 0, 4, 6),      # quarter-of-X spread but bounded drift
+    ],
+    # second pass: G fronts spread evenly over X (each front L2-resident: DRAM ~ G x 8 GB), and
+    # single fronts whose CTAs are de-phased by a few tiles each
+    "fronts": [
+        (64, 256, 0, 0, 6),
+        (8, 8, 0, 2, 5),
+        (16, 16, 0, 2, 4),
+        (32, 32, 0, 1, 3),
+        (4, 4, 0, 2, 6),
+        (2, 2, 0, 4, 6),
+        (64, -8, 0, 2, 6),       # one front, 64 positions 8 tiles apart
+        (256, -3, 0, 2, 6),      # one front, every CTA at its own position 3 tiles apart
+        (16, 16, 0, 1, 4),
+        (8, 8, 0, 4, 4),
+    ],
+}
 
 
 def main():
@@ -45,7 +63,8 @@ def main():
     ap.add_argument("--reps", type=int, default=2)
     ap.add_argument("--no-warm", action="store_true")
     ap.add_argument("--out", default=os.path.join(ROOT, "gpurun_out", "sweep_probe.json"))
-    ap.add_argument("--only", type=int, nargs="*", default=None, help="indices into SCHEDULES")
+    ap.add_argument("--set", default="coherent", choices=sorted(SCHEDULE_SETS))
+    ap.add_argument("--only", type=int, nargs="*", default=None, help="indices into the schedule set")
     args = ap.parse_args()
 
     import gsi_b200 as gsi
@@ -63,7 +82,7 @@ def main():
 
     rows = []
     ref = None
-    for i, (g, d, h, w, es) in enumerate(SCHEDULES):
+    for i, (g, d, h, w, es) in enumerate(SCHEDULE_SETS[args.set]):
         if args.only is not None and i not in args.only:
             continue
         ctx.set_option("kcov.window", 0)
@@ -85,7 +104,7 @@ def main():
         if ref is None:
             ref = y
         dev = float(np.max(np.abs(y - ref)) / np.max(np.abs(ref)))
-        rows.append({"groups": g, "div": d, "hint": h, "window": w, "epoch_shift": es,
+        rows.append({"index": i, "groups": g, "div": d, "hint": h, "window": w, "epoch_shift": es,
                      "launches": nl + (0 if args.no_warm else 1), "ms_per_launch": ms / max(nl, 1),
                      "tflops": fl / (ms * 1e-3) * 1e-12 if ms > 0 else None, "rel_dev_vs_first": dev})
         print(json.dumps(rows[-1]), flush=True)
