@@ -3,8 +3,8 @@
 # `ncu --set full` capture of the product kernel under the picked schedule.
 cd "$GRAFT_REPO_ROOT" 2>/dev/null || cd "$(dirname "$0")/.."
 mkdir -p gpurun_out
-timeout 60 python tools/sweep_probe.py --set fronts --reps 2 --out gpurun_out/sweep_probe2.json > gpurun_out/sweep_probe2.log 2>&1
-echo "probe rc=$?"; tail -12 gpurun_out/sweep_probe2.log
+timeout 60 python tools/sweep_probe.py --set fronts --reps 2 --control --out gpurun_out/sweep_probe2.json > gpurun_out/sweep_probe2.log 2>&1
+echo "probe rc=$?"; tail -14 gpurun_out/sweep_probe2.log
 PICK=$(python tools/pick_schedule.py gpurun_out/sweep_probe2.json 2>/dev/null)
 SW=$(echo "$PICK" | sed -n 1p); IDX=$(echo "$PICK" | sed -n 2p)
 [ -z "$SW" ] && SW="64,256,0,0,6"; [ -z "$IDX" ] && IDX="0 1 2"

@@ -62,6 +62,7 @@ def main():
     ap.add_argument("--workload", default="c3")
     ap.add_argument("--reps", type=int, default=2)
     ap.add_argument("--no-warm", action="store_true")
+    ap.add_argument("--control", action="store_true", help="also time an L2-resident problem (X = 50 MB)")
     ap.add_argument("--out", default=os.path.join(ROOT, "gpurun_out", "sweep_probe.json"))
     ap.add_argument("--set", default="coherent", choices=sorted(SCHEDULE_SETS))
     ap.add_argument("--only", type=int, nargs="*", default=None, help="indices into the schedule set")
@@ -108,9 +109,36 @@ def main():
                      "launches": nl + (0 if args.no_warm else 1), "ms_per_launch": ms / max(nl, 1),
                      "tflops": fl / (ms * 1e-3) * 1e-12 if ms > 0 else None, "rel_dev_vs_first": dev})
         print(json.dumps(rows[-1]), flush=True)
+    control = None
+    if args.control:
+        # Control: the same kernel shape on a problem whose X (50 MB) stays L2-resident whatever the
+        # schedule -- is an X stream served entirely from L2 as fast per k-tile as one served from HBM?
+        X.free(); Y.free(); op.free()
+        cgrid = (32, 32, 28)
+        cn = int(np.prod(cgrid))
+        cop = gsi.GridKernelCovMatrix(kind, cgrid, ell, ctx=ctx)
+        cX = gsi.DeviceMatrix.from_host(ctx, np.random.default_rng(1).standard_normal((cn, l)))
+        cY = gsi.DeviceMatrix(ctx, cn, l)
+        control = []
+        for (g, d, h, w, es) in [(64, 256, 0, 0, 6), (64, -1, 0, 4, 6), (1, 0, 0, 0, 6)]:
+            ctx.set_option("kcov.window", 0)
+            ctx.set_option("kcov.sweep_groups", g)
+            ctx.set_option("kcov.sweep_div", d)
+            ctx.set_option("kcov.epoch_shift", es)
+            ctx.set_option("kcov.window", w)
+            for _ in range(3):
+                gsi._lib.check(lib.gsi_op_apply(cop._h, 0, cX._h, cY._h))
+            ctx.sync()
+            ctx.gemm_timing(enable=True)
+            for _ in range(20):
+                gsi._lib.check(lib.gsi_op_apply(cop._h, 0, cX._h, cY._h))
+            ms, nl, fl = ctx.gemm_timing(enable=False)
+            control.append({"n": cn, "groups": g, "div": d, "window": w, "epoch_shift": es,
+                            "ms_per_launch": ms / nl, "tflops": fl / (ms * 1e-3) * 1e-12})
+            print("control", json.dumps(control[-1]), flush=True)
     os.makedirs(os.path.dirname(args.out), exist_ok=True)
     with open(args.out, "w") as f:
-        json.dump({"workload": desc, "n": n, "l": l, "schedules": rows}, f, indent=1)
+        json.dump({"workload": desc, "n": n, "l": l, "schedules": rows, "l2fit_control": control}, f, indent=1)
 
 
 if __name__ == "__main__":
