@@ -188,27 +188,31 @@ __global__ void __launch_bounds__(KC_THREADS, 1) kcov_gemm_kernel(const __grid_c
         return full_rounds * per_round + b0;
     };
     const int64_t nkt = (p.n + KC_BK - 1) / KC_BK;
-    // De-synchronised (cyclic) k sweeps, GSI_SWEEP="groups,div,hint": CTA b starts its sweep
-    // (b mod groups) * nkt/div tiles into X (default 64 groups over a quarter of X).  Measured on C3
-    // (profiles/r01): +2.5 % over lock-step sweeps (31.8 vs 31.0 TF/s); requests for one X tile no
-    // longer arrive from all 148 SMs at once.  Either way the X stream (366 MB > L2) is served
-    // mostly from HBM once the persistent CTAs have drifted apart: ncu shows ~715 GB read per launch
-    // (L2 hit rate 27 %, 16 % of HBM bandwidth) with the DMMA pipe 91-93 % busy.  Forcing L2
-    // residency (k-chunks of 48 MB with a W read-modify-write per chunk) cost 9-22 % of tensor
-    // throughput and was not kept; cluster multicast of the X tiles is the planned fix.
+    // De-synchronised (cyclic) k sweeps (gsi_ctx_set_option "kcov.sweep_*" / GSI_SWEEP): CTA b starts
+    // its sweep (b mod groups) * separation tiles into X (default 64 groups over a quarter of X).
+    // Measured on C3 (profiles/r01): +2.5 % over lock-step starts.  In this mode the X stream
+    // (366 MB > L2) is served mostly from HBM -- ncu: 610-716 GB read per launch (L2 hit rate
+    // 26-33 %, 17 % of HBM bandwidth) -- with the DMMA pipe 91-93 % busy, 3.95 us per k-tile.
     const int64_t kt_sep = p.sweep_div < 0 ? -(int64_t)p.sweep_div
                            : p.sweep_div == 0 ? 0
                            : (nkt >= p.sweep_div ? nkt / p.sweep_div : (nkt >= 16 ? 1 : 0));
     const int64_t kt0 = ((int64_t)(blockIdx.x & (p.sweep_groups - 1)) * kt_sep) % nkt;
-    // Sweep window (p.win_epochs > 0): the persistent CTAs all stream the same X, but left alone they
-    // drift apart by more than an L2's worth of k-tiles and every CTA ends up streaming X from HBM
-    // (ncu: 716 GB per C3 launch against 0.7 GB algorithmic).  The schedule is static -- the launch
-    // ends with its slowest CTA anyway -- so the producer holds a CTA that is more than win_epochs
-    // epochs ahead of the slowest one: every 2^epoch_shift k-tiles it counts itself into the epoch's
-    // arrival counter and waits until the epoch win_epochs back has been reached by every CTA that
-    // will ever reach it (all CTAs during the full rounds, the tail CTAs afterwards).  The wait is
-    // bounded (KC_SPIN_LIMIT): a CTA that times out -- co-tenancy, a debugger -- drops the window
-    // for the rest of the launch, so the window can cost time but never progress.
+    // Sweep window (p.win_epochs > 0, default off): the persistent CTAs all stream the same X, but
+    // left alone they drift apart by more than an L2's worth of k-tiles.  The schedule is static --
+    // the launch ends with its slowest CTA anyway -- so the producer can hold a CTA that is more than
+    // win_epochs epochs ahead of the slowest one: every 2^epoch_shift k-tiles it counts itself into
+    // the epoch's arrival counter and waits until the epoch win_epochs back has been reached by every
+    // CTA that will ever reach it (all CTAs during the full rounds, the tail CTAs afterwards).  The
+    // wait is bounded (KC_SPIN_LIMIT): a CTA that times out -- co-tenancy, a debugger -- drops the
+    // window for the rest of the launch, so the window can cost time but never progress.
+    // MEASURED (profiles/r01/sweep_schedules_c3_summary.csv, 22 schedules): one coherent front cuts
+    // DRAM traffic 611 GB -> 8.0 GB per launch (= X once per round, L2 hit rate 98.6 %) and products
+    // stay bit-identical, but EVERY L2-served variant -- any window, lock-step or de-phased CTAs,
+    // 2..32 fronts, evict_last -- runs at 589-612 ms (4.5 us per k-tile) against 528-532 ms streamed
+    // from HBM, and so does a problem whose X fits L2 outright; the pacing itself is free (same
+    // window over the quarter-of-X spread: 530 ms).  The HBM-streamed schedule therefore stays the
+    // default; the window is the knob for deployments that must spare HBM bandwidth.  Why the
+    // L2-served stream costs the DMMA pipe ~13 % is the first ncu question of the next round.
     const int64_t full_it = full_rounds * nkt;
     const unsigned n_tail_ctas = q_tail > 0 ? (unsigned)((remaining + q_tail - 1) / q_tail) : 0u;
     bool window_on = p.win_epochs > 0;            // thread 0 only
