@@ -1,0 +1,16 @@
+#!/bin/bash
+# Round-2 opener (needs ~3 GPU-minutes): why is the L2-served X stream 13 % slower than the
+# HBM-streamed one?  Two `ncu --set full` captures of ONE C3 product launch --
+# default schedule (index 0 of the "coherent" set) and one coherent windowed front (index 1) --
+# and the side-by-side digest.
+cd "$GRAFT_REPO_ROOT" 2>/dev/null || cd "$(dirname "$0")/.."
+mkdir -p gpurun_out
+for IDX in 0 1; do
+    timeout 150 ncu --set full --import-source on --clock-control none -k regex:kcov -c 1 -f \
+        -o gpurun_out/prof_kcov_c3_sched$IDX \
+        python tools/sweep_probe.py --set coherent --only $IDX --reps 1 --no-warm \
+        --out gpurun_out/sweep_probe_full$IDX.json > gpurun_out/sweep_probe_full$IDX.log 2>&1
+    echo "capture $IDX rc=$?"
+done
+python tools/ncu_stalls.py gpurun_out/prof_kcov_c3_sched0.ncu-rep gpurun_out/prof_kcov_c3_sched1.ncu-rep \
+    | tee gpurun_out/kcov_l2_question_digest.txt
