@@ -206,17 +206,34 @@ void tsqr_thinQ(gsi_op* op, gsi_buf* Y, bool sharded, double* Rdev) {
     GSI_CUDA(cudaStreamSynchronize(ctx->stream));
 }
 
-static void normalise(gsi_op* op, gsi_buf* Y, bool sharded, int normaliser) {
-    if (normaliser == GSI_NORMALISER_LU_REF) normalise_lu(op, Y, sharded);
-    else tsqr_thinQ(op, Y, sharded, nullptr);
-}
-
 // One product step of the iteration.  `cur` holds the current iterate in distribution
 // `cur_sharded`; returns the product in `out` and its distribution.
 struct Iterate {
     BufPtr buf;
     bool sharded = false;     // true: this rank holds rows [row0, row0+mloc) only
 };
+
+// EXPERIMENTAL (option "lu.replicate", default off): the next product needs the whole iterate on
+// every rank anyway, so gather it BEFORE the LU and let every rank factor all rows redundantly
+// (deterministic kernels: identical factors everywhere, identical to the single-GPU result)
+// instead of exchanging pivot candidates per column.  Pays off only with a fast local LU.
+static void replicate(gsi_op* op, Iterate& it) {
+    gsi_ctx* ctx = op->ctx;
+    if (!(it.sharded && ctx->world > 1)) return;
+    BufPtr full = make_buf(ctx, GSI_LAYOUT_TALL, op->m, it.buf->cols);
+    gather_rows(op, it.buf.get(), full.get());
+    it.buf = std::move(full);
+    it.sharded = false;
+}
+
+static void normalise(gsi_op* op, Iterate& it, int normaliser) {
+    if (normaliser == GSI_NORMALISER_LU_REF) {
+        if (op->ctx->lu_replicate && op->type != OP_DENSE) replicate(op, it);
+        normalise_lu(op, it.buf.get(), it.sharded);
+    } else {
+        tsqr_thinQ(op, it.buf.get(), it.sharded, nullptr);
+    }
+}
 
 static Iterate apply_step(gsi_op* op, int trans, Iterate& cur, BufPtr& full_scratch) {
     gsi_ctx* ctx = op->ctx;
@@ -267,12 +284,12 @@ static Iterate rangefinder_fixed_impl(gsi_op* op, const gsi_buf* Omega, int64_t 
         tsqr_thinQ(op, cur.buf.get(), cur.sharded, nullptr);
         return cur;
     }
-    normalise(op, cur.buf.get(), cur.sharded, normaliser);       // :60-61
+    normalise(op, cur, normaliser);                              // :60-61
     for (int64_t i = 1; i <= q; ++i) {
         Iterate t = apply_step(op, 1, cur, full_scratch);        // Q = A' * Q     :67
-        normalise(op, t.buf.get(), t.sharded, normaliser);       // :68-69
+        normalise(op, t, normaliser);                            // :68-69
         cur = apply_step(op, 0, t, full_scratch);                // Q = A * Q      :70
-        if (i < q) normalise(op, cur.buf.get(), cur.sharded, normaliser);   // :72-73
+        if (i < q) normalise(op, cur, normaliser);               // :72-73
         else tsqr_thinQ(op, cur.buf.get(), cur.sharded, nullptr);           // :75-76
     }
     (void)ctx;

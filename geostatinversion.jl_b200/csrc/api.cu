@@ -202,6 +202,8 @@ GSI_API int32_t gsi_ctx_set_option(gsi_ctx* ctx, const char* name, int64_t value
         else if (n == "kcov.window") ctx->kcov_window = v;
         else if (n == "kcov.epoch_shift") ctx->kcov_epoch_shift = v;
         else if (n == "svd.fused") ctx->svd_fused = v != 0;
+        else if (n == "lu.fused") ctx->lu_fused = v != 0;
+        else if (n == "lu.replicate") ctx->lu_replicate = v != 0;
         else throw Error(GSI_ERR_INVALID_ARGUMENT, "unknown option '" + n + "'");
         try {
             validate_kcov_options(ctx);
@@ -224,6 +226,8 @@ GSI_API int32_t gsi_ctx_get_option(gsi_ctx* ctx, const char* name, int64_t* valu
         else if (n == "kcov.window") *value_out = ctx->kcov_window;
         else if (n == "kcov.epoch_shift") *value_out = ctx->kcov_epoch_shift;
         else if (n == "svd.fused") *value_out = ctx->svd_fused;
+        else if (n == "lu.fused") *value_out = ctx->lu_fused;
+        else if (n == "lu.replicate") *value_out = ctx->lu_replicate;
         else throw Error(GSI_ERR_INVALID_ARGUMENT, "unknown option '" + n + "'");
     });
 }

@@ -92,6 +92,9 @@ struct gsi_ctx {
     // small Jacobi SVD: all sweeps in one cluster launch (svd.cu; gsi_ctx_set_option "svd.fused")
     int svd_fused = 1;
     int* jflags = nullptr;               // [60] rotations per sweep, [60] sweeps used
+    // EXPERIMENTAL, default off, not yet run on hardware (gsi_ctx_set_option "lu.fused" / "lu.replicate"):
+    int lu_fused = 0;                    // panel column steps in one cooperative launch (rows all local)
+    int lu_replicate = 0;                // multi-GPU: gather the iterate and factor it redundantly on every rank
 };
 
 struct gsi_buf {

@@ -22,8 +22,17 @@
 //                         copies (never from memory being rewritten), scale column k,
 //                         rank-1 update of the trailing columns, and -- fused -- the
 //                         arg-max search of column k+1.
+//
+// EXPERIMENTAL (option "lu.fused", default off, single-GPU / replicated iterates only): the
+// column steps of a panel in ONE cooperative launch, lu_panel_fused_kernel -- the same
+// arithmetic per element, one grid-wide barrier per column instead of two kernel boundaries.
+// Every row is written only by the CTA that owns it; the pivot candidates travel with a copy of
+// their row, so nobody reads a row another CTA may be rewriting.  Not yet run on hardware.
 #include "common.cuh"
 #include "algos.h"
+#include <cooperative_groups.h>
+
+namespace cg = cooperative_groups;
 
 namespace gsi {
 
@@ -183,6 +192,139 @@ lu_eliminate_kernel(double* __restrict__ Y, int64_t ld, int64_t nloc, int64_t ro
     }
 }
 
+
+// ---------------------------------------------------------------------------- fused panel
+// One cooperative launch per panel [ps, pe).  CTA b owns rows [b*R, (b+1)*R) (R a multiple of
+// 8).  Buffers (double-buffered by column parity so that a CTA that is already publishing for
+// column k+1 cannot overwrite what a slower CTA still reads for column k; a buffer of a given
+// parity is rewritten only after two grid barriers):
+//   cand [2][G]      best (|value|, row) of each CTA for the current column
+//   rows [2][G][l]   copy of that candidate row (all l columns)
+//   krows[2][l]      copy of row k, published by its owner
+struct LuFusedParams {
+    double* Y; int64_t ld; int64_t n; int l; int ps, pe;
+    Cand* cand; double* rows; double* krows; int* flags;
+    int64_t R;
+};
+
+// (|v|, row) arg-max over the block with LAPACK's tie rule; every thread gets the result.
+__device__ void lu_block_best(double& bv, double& bi, double* sv, double* si) {
+    sv[threadIdx.x] = bv; si[threadIdx.x] = bi;
+    __syncthreads();
+    for (int s = LU_THREADS / 2; s > 0; s >>= 1) {
+        if (threadIdx.x < s) {
+            if (cand_better(sv[threadIdx.x + s], si[threadIdx.x + s], sv[threadIdx.x], si[threadIdx.x])) {
+                sv[threadIdx.x] = sv[threadIdx.x + s]; si[threadIdx.x] = si[threadIdx.x + s];
+            }
+        }
+        __syncthreads();
+    }
+    bv = sv[0]; bi = si[0];
+    __syncthreads();
+}
+
+__global__ void __launch_bounds__(LU_THREADS) lu_panel_fused_kernel(LuFusedParams p) {
+    cg::grid_group grid = cg::this_grid();
+    extern __shared__ double sm[];
+    double* prow = sm;              // pivot row (all l columns)
+    double* krow = sm + p.l;        // previous content of row k
+    __shared__ double sv[LU_THREADS], si[LU_THREADS];
+    const int l = p.l, G = (int)gridDim.x, b = (int)blockIdx.x;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, sub = lane & 3, rsub = lane >> 2;
+    const int64_t r0 = (int64_t)b * p.R;
+    const int64_t r1 = (r0 + p.R < p.n) ? r0 + p.R : p.n;      // my rows [r0, r1) (may be empty)
+    double* Y = p.Y;
+    const int64_t ld = p.ld;
+
+    // publish my candidate (and its row) for column `col`, and row `col` if I own it
+    auto publish = [&](int col, int par, double bv, double bi) {
+        lu_block_best(bv, bi, sv, si);
+        if (threadIdx.x == 0) { p.cand[(size_t)par * G + b].val = bv; p.cand[(size_t)par * G + b].idx = bi; }
+        if (bv >= 0.0) {
+            const double* src = Y + (int64_t)bi * ld;
+            double* dst = p.rows + ((size_t)par * G + b) * l;
+            for (int j = threadIdx.x; j < l; j += LU_THREADS) dst[j] = src[j];
+        }
+        if (col >= r0 && col < r1) {
+            const double* src = Y + (int64_t)col * ld;
+            double* dst = p.krows + (size_t)par * l;
+            for (int j = threadIdx.x; j < l; j += LU_THREADS) dst[j] = src[j];
+        }
+    };
+
+    // ---- candidates of the first column of the panel
+    {
+        double bv = -1.0, bi = 0.0;
+        for (int64_t i = r0 + threadIdx.x; i < r1; i += LU_THREADS) {
+            if (i < p.ps) continue;
+            const double v = fabs(Y[i * ld + p.ps]);
+            if (cand_better(v, (double)i, bv, bi)) { bv = v; bi = (double)i; }
+        }
+        publish(p.ps, 0, bv, bi);
+    }
+    grid.sync();
+
+    for (int k = p.ps; k < p.pe; ++k) {
+        const int par = (k - p.ps) & 1;
+        // ---- global pivot: every CTA reduces the G candidates the same way
+        double bv = -1.0, bi = 0.0;
+        for (int c = threadIdx.x; c < G; c += LU_THREADS) {
+            const double v = p.cand[(size_t)par * G + c].val, i = p.cand[(size_t)par * G + c].idx;
+            if (v >= 0.0 && cand_better(v, i, bv, bi)) { bv = v; bi = i; }
+        }
+        lu_block_best(bv, bi, sv, si);
+        const int64_t piv = (int64_t)bi;
+        const int win = (int)(piv / p.R);                       // the CTA that owns (and published) row piv
+        for (int j = threadIdx.x; j < l; j += LU_THREADS) {
+            prow[j] = p.rows[((size_t)par * G + win) * l + j];
+            krow[j] = p.krows[(size_t)par * l + j];
+        }
+        __syncthreads();
+        const double pivot = prow[k];
+        double rpiv = 0.0;
+        if (pivot == 0.0) {
+            if (b == 0 && threadIdx.x == 0) atomicCAS(&p.flags[0], 0, k + 1);   // first zero pivot (1-based)
+        } else {
+            rpiv = 1.0 / pivot;
+        }
+        const bool use_recip = fabs(pivot) >= 2.2250738585072014e-308;       // dgetf2: sfmin
+        // ---- row interchange, each row by its owner: row k receives the pivot row (all columns);
+        //      the part of old row k that this step does not rewrite moves to position piv
+        if (piv != k) {
+            if (k >= r0 && k < r1)
+                for (int j = threadIdx.x; j < l; j += LU_THREADS) Y[(int64_t)k * ld + j] = prow[j];
+            if (piv >= r0 && piv < r1)
+                for (int j = threadIdx.x; j < l; j += LU_THREADS)
+                    if (j < k || j >= p.pe) Y[piv * ld + j] = krow[j];
+        }
+        // ---- elimination of my rows below k, candidates for column k+1
+        bv = -1.0; bi = 0.0;
+        int64_t lstart = (int64_t)k + 1;
+        if (lstart < r0) lstart = r0;
+        for (int64_t i = lstart + warp * 8 + rsub; i < r1; i += LU_WARPS * 8) {
+            double* yrow = Y + i * ld;
+            const double* src = (i == piv) ? krow : yrow;
+            double m;
+            if (pivot == 0.0) m = src[k];
+            else m = use_recip ? src[k] * rpiv : src[k] / pivot;
+            if (sub == 0) yrow[k] = m;
+            for (int j = k + 1 + sub; j < p.pe; j += 4) {
+                const double v = src[j] - m * prow[j];
+                yrow[j] = v;
+                if (j == k + 1) {
+                    const double a = fabs(v);
+                    if (cand_better(a, (double)i, bv, bi)) { bv = a; bi = (double)i; }
+                }
+            }
+        }
+        if (k + 1 < p.pe) {
+            __syncthreads();                     // my rows are complete before their copies are taken
+            publish(k + 1, par ^ 1, bv, bi);
+            grid.sync();
+        }
+    }
+}
+
 // U12 = L11^{-1} A12 for the panel rows [ps, pe): one thread per trailing column.  The rows are
 // updated in place and copied to the small TALL buffer U (pb x (l - pe)) for the GEMM update.
 __global__ void lu_u12_kernel(double* __restrict__ Y, int64_t ld, int l, int ps, int pe, int64_t lrow_ps,
@@ -236,8 +378,35 @@ void lu_L_inplace(gsi_ctx* ctx, gsi_buf* Y, int64_t row0, int64_t n_global, cons
     const bool own_top = (world == 1) || (ctx->rank == 0);
 
     const size_t smem = 2 * (size_t)l * sizeof(double);
+    // experimental single-launch panels (rows all local): cooperative grid of co-resident CTAs
+    LuFusedParams fp;
+    int fgrid = 0;
+    if (ctx->lu_fused && world == 1) {
+        int occ = 0;
+        GSI_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, lu_panel_fused_kernel, LU_THREADS, smem));
+        fgrid = ctx->num_sms * (occ < 2 ? occ : 2);
+        const int64_t need8 = (nloc + 7) / 8;
+        if (fgrid > need8) fgrid = (int)need8;
+        const size_t fneed = (size_t)2 * fgrid * 2 + (size_t)2 * fgrid * l + 2 * (size_t)l + 16;
+        if (fgrid < 1 || fneed > ctx->scratch_doubles) fgrid = 0;          // fall back to the per-column path
+        if (fgrid > 0) {
+            fp.Y = Y->d; fp.ld = Y->ld; fp.n = nloc; fp.l = l;
+            fp.cand = reinterpret_cast<Cand*>(ctx->scratch);
+            fp.rows = ctx->scratch + (size_t)2 * fgrid * 2;
+            fp.krows = fp.rows + (size_t)2 * fgrid * l;
+            fp.flags = ctx->dflags;
+            fp.R = round_up((nloc + fgrid - 1) / fgrid, 8);
+        }
+    }
     for (int ps = 0; ps < l; ps += pb) {
         const int pe = (ps + pb < l) ? ps + pb : l;
+        if (fgrid > 0) {
+            fp.ps = ps; fp.pe = pe;
+            void* args[] = {&fp};
+            GSI_CUDA(cudaLaunchCooperativeKernel((void*)lu_panel_fused_kernel, dim3((unsigned)fgrid), dim3(LU_THREADS),
+                                                 args, smem, ctx->stream));
+            count_launch(ctx);
+        } else {
         lu_search_kernel<<<grid, LU_THREADS, 0, ctx->stream>>>(Y->d, Y->ld, nloc, row0, ps, cand);
         GSI_CUDA(cudaGetLastError());
         count_launch(ctx);
@@ -254,6 +423,7 @@ void lu_L_inplace(gsi_ctx* ctx, gsi_buf* Y, int64_t row0, int64_t n_global, cons
                                                                           owner_k, cand, ctx->dflags);
             GSI_CUDA(cudaGetLastError());
             count_launch(ctx, 2);
+        }
         }
         if (pe < l) {
             // U12 on the owner of the pivot rows, broadcast, then the rank-pb trailing update

@@ -111,6 +111,10 @@ int32_t gsi_ctx_phase_timing(gsi_ctx* ctx, double* ms_out8, int32_t reset);
  *   "kcov.epoch_shift"   epoch = 2^shift k-tiles of 32 points
  *   "svd.fused"          1 (default): the small Jacobi SVD (<= 512 columns) runs all sweeps in
  *                        one thread-block-cluster launch; 0: one launch per round (same rotations)
+ *   "lu.fused"           EXPERIMENTAL, default 0, not yet verified on hardware: the column
+ *                        steps of an LU panel run in one cooperative launch (rows all local)
+ *   "lu.replicate"       EXPERIMENTAL, default 0: multi-GPU LU_REF normaliser gathers the iterate
+ *                        and factors it redundantly on every rank (no per-column exchange)
  * The environment variable GSI_SWEEP="groups,div,hint[,window[,epoch_shift]]" sets the
  * same knobs at context creation.                                                     */
 int32_t gsi_ctx_set_option(gsi_ctx* ctx, const char* name, int64_t value);

@@ -1,0 +1,84 @@
+"""Parity tests of code paths that are written but NOT yet verified on hardware (opt-in
+options, default off).  They are skipped unless GSI_EXPERIMENTAL=1, so that the default
+`-m gpu` run only exercises verified code:
+
+    GSI_EXPERIMENTAL=1 python -m pytest tests/test_gpu_experimental.py -m gpu -x -q
+"""
+import os
+
+import numpy as np
+import pytest
+
+import oracle
+from gpu_util import gsi, relerr  # noqa: F401
+
+pytestmark = [pytest.mark.gpu,
+              pytest.mark.skipif(os.environ.get("GSI_EXPERIMENTAL") != "1",
+                                 reason="experimental options: set GSI_EXPERIMENTAL=1")]
+
+
+@pytest.mark.parametrize("n,l", [(64, 8), (300, 17), (1000, 60), (5000, 110), (20000, 210), (777, 256), (40, 33)])
+def test_lu_fused_matches_per_column(gsi, n, l):
+    """"lu.fused": the cooperative single-launch panel performs the same pivot choices and the
+    same arithmetic as the launch-per-column path -> bit-identical L; and both match the
+    oracle's dgetrf-based unpermuted L."""
+    from gsi_b200.pcga import lu_L
+    ctx = gsi.default_context()
+    rng = np.random.default_rng(n + l)
+    Y = rng.standard_normal((n, l))
+    saved = ctx.get_option("lu.fused")
+    try:
+        ctx.set_option("lu.fused", 0)
+        L0 = lu_L(Y)
+        ctx.set_option("lu.fused", 1)
+        L1 = lu_L(Y)
+    finally:
+        ctx.set_option("lu.fused", saved)
+    assert np.array_equal(L0, L1)
+    assert relerr(L1, oracle.lu_L_unpermuted(Y)) < 1e-10
+
+
+def test_lu_fused_ties_and_zero_pivot(gsi):
+    """LAPACK tie rule (first row of maximal |value|) and the SingularException mapping."""
+    from gsi_b200.pcga import lu_L
+    ctx = gsi.default_context()
+    Y = np.ones((200, 6))
+    Y[:, 1] = np.arange(200) % 7
+    Y[:, 2] = -(np.arange(200) % 5)
+    Y[:, 3:] = np.random.default_rng(0).integers(-3, 4, size=(200, 3))
+    saved = ctx.get_option("lu.fused")
+    try:
+        ctx.set_option("lu.fused", 1)
+        try:
+            L1 = lu_L(Y)
+            err1 = None
+        except gsi.SingularException as e:
+            L1, err1 = None, e
+        ctx.set_option("lu.fused", 0)
+        try:
+            L0 = lu_L(Y)
+            err0 = None
+        except gsi.SingularException as e:
+            L0, err0 = None, e
+    finally:
+        ctx.set_option("lu.fused", saved)
+    assert (err0 is None) == (err1 is None)
+    if err0 is None:
+        assert np.array_equal(L0, L1)
+
+
+def test_randsvd_with_fused_lu(gsi):
+    grid, ell, K, p, q = (40, 30), [6.0, 4.0], 40, 5, 2
+    coords = oracle.grid_coords(grid)
+    Omega = np.random.default_rng(3).standard_normal((coords.shape[1], K + p))
+    op = gsi.KernelCovMatrix("exponential", coords, ell)
+    ctx = gsi.default_context()
+    saved = ctx.get_option("lu.fused")
+    try:
+        ctx.set_option("lu.fused", 0)
+        Z0 = gsi.randsvd(op, K, p, q, Omega=Omega)
+        ctx.set_option("lu.fused", 1)
+        Z1 = gsi.randsvd(op, K, p, q, Omega=Omega)
+    finally:
+        ctx.set_option("lu.fused", saved)
+    assert np.array_equal(Z0, Z1)
