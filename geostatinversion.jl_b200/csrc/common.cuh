@@ -95,6 +95,7 @@ struct gsi_ctx {
     // EXPERIMENTAL, default off, not yet run on hardware (gsi_ctx_set_option "lu.fused" / "lu.replicate"):
     int lu_fused = 0;                    // panel column steps in one cooperative launch (rows all local)
     int lu_replicate = 0;                // multi-GPU: gather the iterate and factor it redundantly on every rank
+    int qr_fast_house = 0;               // Householder-scalar kernel with a parallel reduction of the partials
 };
 
 struct gsi_buf {

@@ -111,6 +111,59 @@ qr_house_kernel(double* __restrict__ Y, int64_t ld, int ps, int pe, int k, const
     }
 }
 
+// EXPERIMENTAL (option "qr.fast_house", default off, not yet run on hardware): the same step with
+// the reduction of the per-CTA partials spread over all 256 threads (16 slices per column, combined
+// in a fixed order) instead of 16 threads walking all `nparts` partials one after the other -- the
+// serial walk makes the single-CTA kernel 20 us per column (8.6 ms per randsvd at l = 210, and it
+// does not shrink with the row count, i.e. not with the number of GPUs).  Deterministic, but a
+// different summation order than qr_house_kernel (results agree to rounding, not bit for bit).
+__global__ void __launch_bounds__(QP_THREADS)
+qr_house2_kernel(double* __restrict__ Y, int64_t ld, int ps, int pe, int k, const double* __restrict__ partial,
+                 int nparts, double* __restrict__ tw, double* __restrict__ taus, QrScal* __restrict__ scal) {
+    __shared__ double s_red[QP_THREADS / QB][QB];
+    __shared__ double s_g[QB];
+    __shared__ double s_tau, s_scale;
+    {
+        const int c = threadIdx.x % QB, slice = threadIdx.x / QB;          // 16 slices x 16 columns
+        double s = 0.0;
+        for (int b = slice; b < nparts; b += QP_THREADS / QB) s += partial[(size_t)b * QB + c];
+        s_red[slice][c] = s;
+    }
+    __syncthreads();
+    if (threadIdx.x < QB) {
+        double s = 0.0;
+#pragma unroll
+        for (int sl = 0; sl < QP_THREADS / QB; ++sl) s += s_red[sl][threadIdx.x];
+        s_g[threadIdx.x] = s;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const double alpha = Y[(int64_t)k * ld + k];
+        const double xnorm2 = s_g[k - ps];
+        double tau = 0.0, scale = 0.0, beta = alpha;
+        if (xnorm2 > 0.0) {
+            const double nrm = sqrt(alpha * alpha + xnorm2);
+            beta = (alpha >= 0.0) ? -nrm : nrm;
+            tau = (beta - alpha) / beta;
+            scale = 1.0 / (alpha - beta);
+        }
+        Y[(int64_t)k * ld + k] = beta;
+        taus[k] = tau;
+        s_tau = tau; s_scale = scale;
+        scal->tau = tau; scal->scale = scale; scal->beta = beta;
+    }
+    __syncthreads();
+    const double tau = s_tau, scale = s_scale;
+    const int j = k + 1 + threadIdx.x;
+    if (j < pe) {
+        const double ykj = Y[(int64_t)k * ld + j];
+        const double w = ykj + scale * s_g[j - ps];         // v' * Y[:, j]   (v_k = 1)
+        const double t = tau * w;
+        Y[(int64_t)k * ld + j] = ykj - t;
+        tw[j - ps] = t;
+    }
+}
+
 // rows i > k: Y[i,k] <- v_i = scale*Y[i,k]; Y[i,j] -= v_i*tw[j] for panel columns j > k;
 // fused: dot products of the new column k+1 with the panel columns (rows > k+1).
 __global__ void __launch_bounds__(QP_THREADS)
@@ -419,7 +472,10 @@ void qr_thinQ_inplace(gsi_ctx* ctx, gsi_buf* Y, double* Rdev) {
         double* T = Tall + (size_t)pi * QB * QB;
         qr_panel_dots_kernel<<<grid, QP_THREADS, 0, st>>>(Y->d, Y->ld, n, ps, pe, partial);
         for (int k = ps; k < pe; ++k) {
-            qr_house_kernel<<<1, QP_THREADS, 0, st>>>(Y->d, Y->ld, ps, pe, k, partial, grid, tw, taus, scal);
+            if (ctx->qr_fast_house)
+                qr_house2_kernel<<<1, QP_THREADS, 0, st>>>(Y->d, Y->ld, ps, pe, k, partial, grid, tw, taus, scal);
+            else
+                qr_house_kernel<<<1, QP_THREADS, 0, st>>>(Y->d, Y->ld, ps, pe, k, partial, grid, tw, taus, scal);
             qr_update_kernel<<<grid, QP_THREADS, 0, st>>>(Y->d, Y->ld, n, ps, pe, k, tw, scal, partial);
         }
         GSI_CUDA(cudaGetLastError());

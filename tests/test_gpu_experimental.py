@@ -82,3 +82,27 @@ def test_randsvd_with_fused_lu(gsi):
     finally:
         ctx.set_option("lu.fused", saved)
     assert np.array_equal(Z0, Z1)
+
+
+@pytest.mark.parametrize("n,l", [(64, 8), (1000, 60), (20000, 210), (300, 256), (5000, 33)])
+def test_qr_fast_house(gsi, n, l):
+    """"qr.fast_house": same Householder QR with a parallel reduction of the partial dot products
+    (different, still deterministic, summation order): orthonormal Q spanning range(Y), R equal
+    to the default path's to rounding."""
+    from gsi_b200.pcga import qr_thinQ
+    ctx = gsi.default_context()
+    rng = np.random.default_rng(n * 3 + l)
+    Y = rng.standard_normal((n, l)) * (10.0 ** (-4 * np.arange(l) / max(l - 1, 1)))[None, :]
+    saved = ctx.get_option("qr.fast_house")
+    try:
+        ctx.set_option("qr.fast_house", 0)
+        Q0, R0 = qr_thinQ(Y, return_R=True)
+        ctx.set_option("qr.fast_house", 1)
+        Q1, R1 = qr_thinQ(Y, return_R=True)
+        Q1b = qr_thinQ(Y)
+    finally:
+        ctx.set_option("qr.fast_house", saved)
+    assert np.array_equal(Q1, Q1b)                                  # deterministic
+    assert np.max(np.abs(Q1.T @ Q1 - np.eye(l))) < 1e-12
+    assert relerr(Q1 @ R1, Y) < 1e-13
+    assert relerr(R1, R0) < 1e-11 and relerr(Q1, Q0) < 1e-9
