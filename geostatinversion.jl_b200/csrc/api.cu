@@ -85,6 +85,48 @@ static void validate_kcov_options(const gsi_ctx* ctx) {
                 "kcov.epoch_shift must be in [2, 16]");
 }
 
+static void set_option_impl(gsi_ctx* ctx, const std::string& n, int64_t value) {
+    const int v = (int)value;
+    const int saved[5] = {ctx->kcov_sweep_groups, ctx->kcov_sweep_div, ctx->kcov_l2_hint, ctx->kcov_window,
+                          ctx->kcov_epoch_shift};
+    if (n == "kcov.sweep_groups") ctx->kcov_sweep_groups = v;
+    else if (n == "kcov.sweep_div") ctx->kcov_sweep_div = v;
+    else if (n == "kcov.l2_hint") ctx->kcov_l2_hint = v;
+    else if (n == "kcov.window") ctx->kcov_window = v;
+    else if (n == "kcov.epoch_shift") ctx->kcov_epoch_shift = v;
+    else if (n == "svd.fused") ctx->svd_fused = v != 0;
+    else if (n == "lu.fused") ctx->lu_fused = v != 0;
+    else if (n == "lu.replicate") ctx->lu_replicate = v != 0;
+    else if (n == "qr.fast_house") ctx->qr_fast_house = v != 0;
+    else throw Error(GSI_ERR_INVALID_ARGUMENT, "unknown option '" + n + "'");
+    try {
+        validate_kcov_options(ctx);
+    } catch (...) {
+        ctx->kcov_sweep_groups = saved[0]; ctx->kcov_sweep_div = saved[1]; ctx->kcov_l2_hint = saved[2];
+        ctx->kcov_window = saved[3]; ctx->kcov_epoch_shift = saved[4];
+        throw;
+    }
+}
+
+// GSI_OPTIONS="name=value,name=value": the gsi_ctx_set_option knobs from the environment
+static void options_from_env(gsi_ctx* ctx) {
+    const char* e = getenv("GSI_OPTIONS");
+    if (!e) return;
+    std::string all(e);
+    size_t pos = 0;
+    while (pos < all.size()) {
+        size_t end = all.find(',', pos);
+        if (end == std::string::npos) end = all.size();
+        const std::string item = all.substr(pos, end - pos);
+        pos = end + 1;
+        if (item.empty()) continue;
+        const size_t eq = item.find('=');
+        GSI_REQUIRE(eq != std::string::npos && eq > 0 && eq + 1 < item.size(), GSI_ERR_INVALID_ARGUMENT,
+                    "GSI_OPTIONS: expected name=value, got '" + item + "'");
+        set_option_impl(ctx, item.substr(0, eq), strtoll(item.c_str() + eq + 1, nullptr, 10));
+    }
+}
+
 static void use(gsi_ctx* ctx) {
     GSI_REQUIRE(ctx != nullptr, GSI_ERR_INVALID_ARGUMENT, "null context");
     GSI_CUDA(cudaSetDevice(ctx->device));
@@ -137,6 +179,7 @@ GSI_API int32_t gsi_ctx_create(int32_t device, int32_t rank, int32_t world, cons
             sscanf(e, "%d,%d,%d,%d,%d", &ctx->kcov_sweep_groups, &ctx->kcov_sweep_div, &ctx->kcov_l2_hint,
                    &ctx->kcov_window, &ctx->kcov_epoch_shift);
         validate_kcov_options(ctx.get());
+        options_from_env(ctx.get());
         if (world > 1) comm_init(ctx.get(), unique_id128);
         *out = ctx.release();
     });
@@ -192,27 +235,7 @@ GSI_API int32_t gsi_ctx_set_option(gsi_ctx* ctx, const char* name, int64_t value
     return guarded([&] {
         use(ctx);
         GSI_REQUIRE(name != nullptr, GSI_ERR_INVALID_ARGUMENT, "null option name");
-        const std::string n(name);
-        const int v = (int)value;
-        const int saved[5] = {ctx->kcov_sweep_groups, ctx->kcov_sweep_div, ctx->kcov_l2_hint, ctx->kcov_window,
-                              ctx->kcov_epoch_shift};
-        if (n == "kcov.sweep_groups") ctx->kcov_sweep_groups = v;
-        else if (n == "kcov.sweep_div") ctx->kcov_sweep_div = v;
-        else if (n == "kcov.l2_hint") ctx->kcov_l2_hint = v;
-        else if (n == "kcov.window") ctx->kcov_window = v;
-        else if (n == "kcov.epoch_shift") ctx->kcov_epoch_shift = v;
-        else if (n == "svd.fused") ctx->svd_fused = v != 0;
-        else if (n == "lu.fused") ctx->lu_fused = v != 0;
-        else if (n == "lu.replicate") ctx->lu_replicate = v != 0;
-        else if (n == "qr.fast_house") ctx->qr_fast_house = v != 0;
-        else throw Error(GSI_ERR_INVALID_ARGUMENT, "unknown option '" + n + "'");
-        try {
-            validate_kcov_options(ctx);
-        } catch (...) {
-            ctx->kcov_sweep_groups = saved[0]; ctx->kcov_sweep_div = saved[1]; ctx->kcov_l2_hint = saved[2];
-            ctx->kcov_window = saved[3]; ctx->kcov_epoch_shift = saved[4];
-            throw;
-        }
+        set_option_impl(ctx, name, value);
     });
 }
 
