@@ -407,23 +407,23 @@ void lu_L_inplace(gsi_ctx* ctx, gsi_buf* Y, int64_t row0, int64_t n_global, cons
                                                  args, smem, ctx->stream));
             count_launch(ctx);
         } else {
-        lu_search_kernel<<<grid, LU_THREADS, 0, ctx->stream>>>(Y->d, Y->ld, nloc, row0, ps, cand);
-        GSI_CUDA(cudaGetLastError());
-        count_launch(ctx);
-        for (int k = ps; k < pe; ++k) {
-            lu_pack_kernel<<<1, LU_THREADS, 0, ctx->stream>>>(Y->d, Y->ld, nloc, row0, l, k, cand, grid, send);
+            lu_search_kernel<<<grid, LU_THREADS, 0, ctx->stream>>>(Y->d, Y->ld, nloc, row0, ps, cand);
             GSI_CUDA(cudaGetLastError());
-            int owner_k = 0;
-            if (world > 1) {
-                comm_allgather(ctx, send, recv, stride * sizeof(double));
-                for (int r = 0; r < world; ++r)
-                    if (k >= part_row0[r] && k < part_row0[r + 1]) owner_k = r;
+            count_launch(ctx);
+            for (int k = ps; k < pe; ++k) {
+                lu_pack_kernel<<<1, LU_THREADS, 0, ctx->stream>>>(Y->d, Y->ld, nloc, row0, l, k, cand, grid, send);
+                GSI_CUDA(cudaGetLastError());
+                int owner_k = 0;
+                if (world > 1) {
+                    comm_allgather(ctx, send, recv, stride * sizeof(double));
+                    for (int r = 0; r < world; ++r)
+                        if (k >= part_row0[r] && k < part_row0[r + 1]) owner_k = r;
+                }
+                lu_eliminate_kernel<<<grid, LU_THREADS, smem, ctx->stream>>>(Y->d, Y->ld, nloc, row0, l, k, pe, recv, world,
+                                                                              owner_k, cand, ctx->dflags);
+                GSI_CUDA(cudaGetLastError());
+                count_launch(ctx, 2);
             }
-            lu_eliminate_kernel<<<grid, LU_THREADS, smem, ctx->stream>>>(Y->d, Y->ld, nloc, row0, l, k, pe, recv, world,
-                                                                          owner_k, cand, ctx->dflags);
-            GSI_CUDA(cudaGetLastError());
-            count_launch(ctx, 2);
-        }
         }
         if (pe < l) {
             // U12 on the owner of the pivot rows, broadcast, then the rank-pb trailing update

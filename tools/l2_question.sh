@@ -14,3 +14,7 @@ for IDX in 0 1; do
 done
 python tools/ncu_stalls.py gpurun_out/prof_kcov_c3_sched0.ncu-rep gpurun_out/prof_kcov_c3_sched1.ncu-rep \
     | tee gpurun_out/kcov_l2_question_digest.txt
+# Does the penalty need the lattice-table look-ups?  Same two schedules with arithmetic generation.
+timeout 60 python tools/sweep_probe.py --set coherent --only 0 1 --generation arithmetic --reps 2 \
+    --out gpurun_out/sweep_probe_arith.json > gpurun_out/sweep_probe_arith.log 2>&1
+echo "arith probe rc=$?"; tail -3 gpurun_out/sweep_probe_arith.log

@@ -63,6 +63,9 @@ def main():
     ap.add_argument("--reps", type=int, default=2)
     ap.add_argument("--no-warm", action="store_true")
     ap.add_argument("--control", action="store_true", help="also time an L2-resident problem (X = 50 MB)")
+    ap.add_argument("--generation", default="table", choices=["table", "arithmetic"],
+                    help="kernel values from the lattice table (default) or from coordinates (no table look-ups "
+                         "on the L2 return path: separates the two suspects of the L2-served-stream penalty)")
     ap.add_argument("--out", default=os.path.join(ROOT, "gpurun_out", "sweep_probe.json"))
     ap.add_argument("--set", default="coherent", choices=sorted(SCHEDULE_SETS))
     ap.add_argument("--only", type=int, nargs="*", default=None, help="indices into the schedule set")
@@ -73,7 +76,11 @@ def main():
     l = K + p
     n = int(np.prod(grid))
     ctx = gsi.default_context()
-    op = gsi.GridKernelCovMatrix(kind, grid, ell, ctx=ctx)
+    if args.generation == "table":
+        op = gsi.GridKernelCovMatrix(kind, grid, ell, ctx=ctx)
+    else:
+        from bench import grid_coords
+        op = gsi.KernelCovMatrix(kind, grid_coords(grid), ell, ctx=ctx)
     X = gsi.DeviceMatrix.from_host(ctx, np.random.default_rng(0).standard_normal((n, l)))
     Y = gsi.DeviceMatrix(ctx, n, l)
     lib = ctx._lib
@@ -138,7 +145,8 @@ def main():
             print("control", json.dumps(control[-1]), flush=True)
     os.makedirs(os.path.dirname(args.out), exist_ok=True)
     with open(args.out, "w") as f:
-        json.dump({"workload": desc, "n": n, "l": l, "schedules": rows, "l2fit_control": control}, f, indent=1)
+        json.dump({"workload": desc, "n": n, "l": l, "generation": args.generation, "schedules": rows,
+                   "l2fit_control": control}, f, indent=1)
 
 
 if __name__ == "__main__":
