@@ -96,6 +96,7 @@ struct gsi_ctx {
     int lu_fused = 0;                    // panel column steps in one cooperative launch (rows all local)
     int lu_replicate = 0;                // multi-GPU: gather the iterate and factor it redundantly on every rank
     int qr_fast_house = 0;               // Householder-scalar kernel with a parallel reduction of the partials
+    int kcov_pace = 0;                   // > 1: X tiles of the structured-grid product kernel fetched in 4 paced chunks
 };
 
 struct gsi_buf {

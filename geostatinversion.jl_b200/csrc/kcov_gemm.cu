@@ -132,7 +132,11 @@ __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
     asm volatile("bar.sync %0, %1;" :: "r"(id), "r"(nthreads) : "memory");
 }
 
-template <int NB, int KIND, int DIM>
+// PACE > 1 (EXPERIMENTAL, option "kcov.pace", structured-grid operator only, not yet run on
+// hardware): the X tile of the next k-tile is fetched as PACE bulk copies issued 8/PACE k-steps
+// apart instead of one 56 KB copy -- a probe for the L2-served-stream penalty (does the burst with
+// which an L2 hit lands in shared memory cost the MMA warps their fragment loads?).
+template <int NB, int KIND, int DIM, int PACE = 1>
 __global__ void __launch_bounds__(KC_THREADS, 1) kcov_gemm_kernel(const __grid_constant__ KcovParams p) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     constexpr int ld = NB * 8 + 4;
@@ -245,7 +249,8 @@ __global__ void __launch_bounds__(KC_THREADS, 1) kcov_gemm_kernel(const __grid_c
         double* xs = smem + (size_t)s * stage_doubles;
         double* us = xs + KC_BK * ld;
         mbar_expect_tx(&full[s], stage_bytes);
-        if (p.l2_hint) bulk_g2s_hint(xs, p.X + kt * KC_BK * p.ld, KC_BK * ld * 8, &full[s], xpolicy);
+        if (PACE > 1) bulk_g2s(xs, p.X + kt * KC_BK * p.ld, (KC_BK / PACE) * ld * 8, &full[s]);     // chunk 0
+        else if (p.l2_hint) bulk_g2s_hint(xs, p.X + kt * KC_BK * p.ld, KC_BK * ld * 8, &full[s], xpolicy);
         else bulk_g2s(xs, p.X + kt * KC_BK * p.ld, KC_BK * ld * 8, &full[s]);
         const int64_t ktn = (kt + 1 == nkt) ? 0 : kt + 1;      // coordinates of the NEXT k-tile ride along
         if (KIND == KC_KIND_TABLE) {
@@ -257,8 +262,20 @@ __global__ void __launch_bounds__(KC_THREADS, 1) kcov_gemm_kernel(const __grid_c
                 bulk_g2s(us + k * KC_BK, p.u + k * p.n_pad + ktn * KC_BK, KC_BK * 8, &full[s]);
         }
     };
+    // chunk c (1 .. PACE-1) of the X tile whose chunk 0 `produce(nxt)` has already issued
+    auto produce_chunk = [&](int64_t nxt, int c) {
+        const int s = (int)(nxt % nstages);
+        int64_t kt = nxt % nkt + kt0;
+        if (kt >= nkt) kt -= nkt;
+        constexpr int chunk = (KC_BK / (PACE > 1 ? PACE : 1)) * ld;          // doubles
+        bulk_g2s(smem + (size_t)s * stage_doubles + c * chunk, p.X + kt * KC_BK * p.ld + c * chunk, chunk * 8, &full[s]);
+    };
     if (tid == 0) {
-        for (int64_t i = 0; i < lookahead && i < total_it; ++i) produce(i);
+        for (int64_t i = 0; i < lookahead && i < total_it; ++i) {
+            produce(i);
+            if (PACE > 1)
+                for (int c = 1; c < PACE; ++c) produce_chunk(i, c);
+        }
     }
 
     const int g = lane >> 2;      // fragment row (A, C) / column (B)
@@ -379,6 +396,9 @@ __global__ void __launch_bounds__(KC_THREADS, 1) kcov_gemm_kernel(const __grid_c
             const double* arow1 = arow0 + 8 * KC_AP;
 #pragma unroll
             for (int ks = 0; ks < KC_BK / 4; ++ks) {
+                if (PACE > 1 && tid == 0 && ks > 0 && ks % (KC_BK / 4 / (PACE > 1 ? PACE : 1)) == 0 &&
+                    it + lookahead < total_it)
+                    produce_chunk(it + lookahead, ks / (KC_BK / 4 / (PACE > 1 ? PACE : 1)));
                 // one kernel value of the NEXT k-tile every second k-step: a single exp chain
                 // is live at a time and its DFMAs interleave with this step's DMMAs
                 if (KIND != KC_KIND_TABLE && (ks & 1) == 0 && gen_next) {
@@ -443,7 +463,7 @@ __global__ void __launch_bounds__(KC_THREADS, 1) kcov_gemm_kernel(const __grid_c
     }
 }
 
-template <int NB, int KIND, int DIM>
+template <int NB, int KIND, int DIM, int PACE = 1>
 static void launch_kcov(gsi_ctx* ctx, const KcovParams& p0) {
     KcovParams p = p0;
     const int ld = NB * 8 + 4;
@@ -454,7 +474,7 @@ static void launch_kcov(gsi_ctx* ctx, const KcovParams& p0) {
     if (stages < 2) stages = 2;
     p.stages = stages;
     const size_t smem = stages * stage_bytes + a_bytes + (2 * stages + 4) * sizeof(uint64_t) + 64 * sizeof(double);
-    auto kfn = kcov_gemm_kernel<NB, KIND, DIM>;
+    auto kfn = kcov_gemm_kernel<NB, KIND, DIM, PACE>;
     GSI_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int occ = 0;
     GSI_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kfn, KC_THREADS, smem));
@@ -487,6 +507,11 @@ static void launch_kcov(gsi_ctx* ctx, const KcovParams& p0) {
 
 template <int NB, int KIND>
 static void dispatch_dim(gsi_ctx* ctx, const KcovParams& p, int dim) {
+    if (KIND == KC_KIND_TABLE && ctx->kcov_pace > 1) {          // experimental paced X fetch (4 chunks)
+        if (dim <= 2) launch_kcov<NB, KIND, 2, (KIND == KC_KIND_TABLE ? 4 : 1)>(ctx, p);
+        else launch_kcov<NB, KIND, 3, (KIND == KC_KIND_TABLE ? 4 : 1)>(ctx, p);
+        return;
+    }
     if (dim <= 2) launch_kcov<NB, KIND, 2>(ctx, p);
     else launch_kcov<NB, KIND, 3>(ctx, p);
 }

@@ -117,6 +117,8 @@ int32_t gsi_ctx_phase_timing(gsi_ctx* ctx, double* ms_out8, int32_t reset);
  *                        and factors it redundantly on every rank (no per-column exchange)
  *   "qr.fast_house"      EXPERIMENTAL, default 0: Householder-scalar step of the QR panels with a
  *                        parallel (still deterministic) reduction of the per-CTA partial sums
+ *   "kcov.pace"          EXPERIMENTAL, default 0: > 1 fetches each X tile of the structured-grid
+ *                        product kernel as 4 bulk copies spread over the k-steps (burst probe)
  * The environment variables GSI_SWEEP="groups,div,hint[,window[,epoch_shift]]" and
  * GSI_OPTIONS="name=value,name=value" set the same knobs at context creation.         */
 int32_t gsi_ctx_set_option(gsi_ctx* ctx, const char* name, int64_t value);

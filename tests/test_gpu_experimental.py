@@ -106,3 +106,32 @@ def test_qr_fast_house(gsi, n, l):
     assert np.max(np.abs(Q1.T @ Q1 - np.eye(l))) < 1e-12
     assert relerr(Q1 @ R1, Y) < 1e-13
     assert relerr(R1, R0) < 1e-11 and relerr(Q1, Q0) < 1e-9
+
+
+def test_kcov_paced_fetch_is_bit_identical(gsi):
+    """"kcov.pace": the X tile arrives in four paced bulk copies instead of one -- only the
+    arrival changes, the accumulation order does not."""
+    ctx = gsi.default_context()
+    grid, ell, l = (110, 109), [7.0, 5.0], 24
+    n = grid[0] * grid[1]
+    X = np.random.default_rng(5).standard_normal((n, l))
+    op = gsi.GridKernelCovMatrix("exponential", grid, ell)
+    saved = {k: ctx.get_option(k) for k in ("kcov.pace", "kcov.window", "kcov.sweep_div")}
+    try:
+        ctx.set_option("kcov.pace", 0)
+        Y0 = op @ X
+        ctx.set_option("kcov.pace", 4)
+        Y1 = op @ X
+        ctx.set_option("kcov.sweep_div", -1)
+        ctx.set_option("kcov.window", 2)
+        Y2 = op @ X
+        ctx.set_option("kcov.pace", 0)
+        Y3 = op @ X
+    finally:
+        for k, v in saved.items():
+            ctx.set_option(k, v)
+    assert np.array_equal(Y0, Y1)
+    assert np.array_equal(Y2, Y3)
+    coords = oracle.grid_coords(grid)
+    rows = np.random.default_rng(6).choice(n, 100, replace=False)
+    assert relerr(Y1[rows], oracle.kernel_cov_dense(0, coords, ell, rows=rows) @ X) < 1e-12

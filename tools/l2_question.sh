@@ -18,3 +18,8 @@ python tools/ncu_stalls.py gpurun_out/prof_kcov_c3_sched0.ncu-rep gpurun_out/pro
 timeout 60 python tools/sweep_probe.py --set coherent --only 0 1 --generation arithmetic --reps 2 \
     --out gpurun_out/sweep_probe_arith.json > gpurun_out/sweep_probe_arith.log 2>&1
 echo "arith probe rc=$?"; tail -3 gpurun_out/sweep_probe_arith.log
+# Is it the burst with which an L2 hit lands in shared memory?  Same two schedules, X tiles in 4 paced chunks
+# (run tests/test_gpu_experimental.py::test_kcov_paced_fetch_is_bit_identical first).
+timeout 60 python tools/sweep_probe.py --set coherent --only 0 1 --pace 4 --reps 2 \
+    --out gpurun_out/sweep_probe_paced.json > gpurun_out/sweep_probe_paced.log 2>&1
+echo "paced probe rc=$?"; tail -3 gpurun_out/sweep_probe_paced.log
