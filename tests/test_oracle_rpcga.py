@@ -138,3 +138,45 @@ def test_lsqr_matches_scipy():
     xs = spla.lsqr(A, b, atol=1.49e-8, btol=1.49e-8, conlim=1 / 1.49e-8, iter_lim=40)[0]
     assert np.linalg.norm(x - xs) / np.linalg.norm(xs) < 1e-6
     assert np.linalg.norm(x - np.linalg.lstsq(A, b, rcond=None)[0]) < 1e-6
+
+
+def test_pinv_cutoff_is_julias():
+    """oracle.pinv = Julia `pinv(A)`: SVD with singular values <= eps*min(size)*sigma_max
+    dropped (atol = 0).  Checked on a matrix with a prescribed spectrum straddling the cut-off."""
+    rng = np.random.default_rng(4)
+    m = 30
+    U, _ = np.linalg.qr(rng.standard_normal((m, m)))
+    V, _ = np.linalg.qr(rng.standard_normal((m, m)))
+    eps = np.finfo(float).eps
+    sig = np.ones(m)
+    sig[-3:] = [1e-6, 1e-3 * eps * m, 0.0]                   # kept, dropped, dropped
+    A = (U * sig) @ V.T
+    P = oracle.pinv(A)
+    keep = sig > eps * m * sig.max()
+    assert keep.sum() == m - 2
+    Pexp = (V[:, keep] / sig[keep]) @ U[:, keep].T
+    assert np.linalg.norm(P - Pexp) / np.linalg.norm(Pexp) < 1e-8
+    assert np.linalg.matrix_rank(P, tol=1e-3) == m - 2
+
+
+def test_pcgadirect_system_is_what_the_iteration_solves():
+    """pcgadirect_system (src/direct.jl:39-57) + pinv (:58) + update (:59-65) == pcgadirectiteration,
+    and bigA equals the dense form of the matrix-free PCGALowRankMatrix the LSQR path uses."""
+    rng = np.random.default_rng(6)
+    N, M = 32, 4
+    x = rng.standard_normal(N)
+    forward = lambda p: p * x
+    xis = [rng.standard_normal(N) for _ in range(M)]
+    X, s0 = np.ones(N), np.full(N, 2.0)
+    R = 1e-8 * np.ones(N)
+    y = forward(rng.standard_normal(N) + 2.0)
+    delta = float(np.sqrt(np.finfo(float).eps))
+    bigA, b, E = oracle.pcgadirect_system(forward, s0, X, xis, R, y, delta)
+    assert bigA.shape == (N + 1, N + 1) and np.array_equal(bigA, bigA.T)
+    HX = bigA[:N, N]
+    assert np.allclose(bigA, oracle.PCGALowRankMatrix(list(E.T), HX, R).dense(), rtol=1e-14, atol=0)
+    xsol = oracle.pinv(bigA) @ b
+    s1 = X * xsol[-1]
+    for i in range(M):
+        s1 = s1 + xis[i] * np.dot(E[:, i], xsol[:-1])
+    assert np.array_equal(s1, oracle.pcgadirectiteration(forward, s0, X, xis, R, y, delta, lambda s, o: None))
