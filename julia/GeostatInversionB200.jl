@@ -202,7 +202,7 @@ splitR(R::AbstractVector, nobs) = (Vector{Float64}(R), nothing)
 splitR(R::LinearAlgebra.Diagonal, nobs) = (Vector{Float64}(R.diag), nothing)
 function splitR(R::SparseArrays.SparseMatrixCSC, nobs)
 	d = Vector{Float64}(LinearAlgebra.diag(R))
-	return SparseArrays.nnz(R - SparseArrays.spdiagm(0=>d)) == 0 ? (d, nothing) : (nothing, Matrix{Float64}(R))
+	return SparseArrays.nnz(SparseArrays.dropzeros(R - SparseArrays.spdiagm(0=>d))) == 0 ? (d, nothing) : (nothing, Matrix{Float64}(R))
 end
 splitR(R::AbstractMatrix, nobs) = (nothing, Matrix{Float64}(R))
 
