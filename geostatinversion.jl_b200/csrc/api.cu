@@ -99,6 +99,7 @@ static void set_option_impl(gsi_ctx* ctx, const std::string& n, int64_t value) {
     else if (n == "lu.replicate") ctx->lu_replicate = v != 0;
     else if (n == "qr.fast_house") ctx->qr_fast_house = v != 0;
     else if (n == "kcov.pace") ctx->kcov_pace = v;
+    else if (n == "kcov.prefetch") ctx->kcov_prefetch = v < 0 ? 0 : (v > 4096 ? 4096 : v);
     else throw Error(GSI_ERR_INVALID_ARGUMENT, "unknown option '" + n + "'");
     try {
         validate_kcov_options(ctx);
@@ -255,6 +256,7 @@ GSI_API int32_t gsi_ctx_get_option(gsi_ctx* ctx, const char* name, int64_t* valu
         else if (n == "lu.replicate") *value_out = ctx->lu_replicate;
         else if (n == "qr.fast_house") *value_out = ctx->qr_fast_house;
         else if (n == "kcov.pace") *value_out = ctx->kcov_pace;
+        else if (n == "kcov.prefetch") *value_out = ctx->kcov_prefetch;
         else throw Error(GSI_ERR_INVALID_ARGUMENT, "unknown option '" + n + "'");
     });
 }

@@ -97,6 +97,7 @@ struct gsi_ctx {
     int lu_replicate = 0;                // multi-GPU: gather the iterate and factor it redundantly on every rank
     int qr_fast_house = 0;               // Householder-scalar kernel with a parallel reduction of the partials
     int kcov_pace = 0;                   // > 1: X tiles of the structured-grid product kernel fetched in 4 paced chunks
+    int kcov_prefetch = 0;               // > 0: L2 bulk prefetch of the X tile this many k-tiles ahead of the sweep
 };
 
 struct gsi_buf {

@@ -43,6 +43,7 @@ struct KcovParams {
     const double* table;   // k(r2) for every lattice offset: table[dx + nx*(dy + ny*dz)]
     int nx, ny;
     int sweep_groups, sweep_div, l2_hint;   // k-sweep de-synchronisation (power-of-two groups, spread = groups/div of X)
+    int pref_ahead;                         // PREF variant: L2 prefetch distance in k-tiles (sits in what was padding)
     unsigned int* sync_cnt;                 // sweep window: arrivals per epoch (zeroed before the launch)
     int win_epochs, epoch_shift;            // a CTA runs at most win_epochs epochs of 2^epoch_shift k-tiles ahead of the slowest
     int64_t n;             // columns of C (= rows of X)
@@ -132,11 +133,19 @@ __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
     asm volatile("bar.sync %0, %1;" :: "r"(id), "r"(nthreads) : "memory");
 }
 
-// PACE > 1 (EXPERIMENTAL, option "kcov.pace", structured-grid operator only, not yet run on
-// hardware): the X tile of the next k-tile is fetched as PACE bulk copies issued 8/PACE k-steps
-// apart instead of one 56 KB copy -- a probe for the L2-served-stream penalty (does the burst with
-// which an L2 hit lands in shared memory cost the MMA warps their fragment loads?).
-template <int NB, int KIND, int DIM, int PACE = 1>
+// EXPERIMENTAL variants (structured-grid operator only, not yet run on hardware; the default
+// instantiations PACE = 1, PREF = 0 compile to the same SASS as before they were added):
+//   PACE > 1 (option "kcov.pace"): the X tile of the next k-tile is fetched as PACE bulk copies
+//     issued 8/PACE k-steps apart instead of one 56 KB copy -- a probe for the L2-served-stream
+//     penalty (does the burst with which an L2 hit lands in shared memory cost the MMA warps
+//     their fragment loads?);
+//   PREF = 1 (option "kcov.prefetch" = tiles ahead): the producer also issues an L2 bulk prefetch
+//     of the X tile `pref_ahead` k-tiles further down its sweep.  Shared memory has room for one
+//     tile of look-ahead only (3 stages of 56 KB), and 5 % of the warp samples of the default
+//     launch wait on the `full` barrier, i.e. on HBM latency tails; with the prefetch the copy
+//     into shared memory is an L2 hit.  It doubles as the cleanest test of the penalty: default
+//     schedule, every fill an L2 hit.
+template <int NB, int KIND, int DIM, int PACE = 1, int PREF = 0>
 __global__ void __launch_bounds__(KC_THREADS, 1) kcov_gemm_kernel(const __grid_constant__ KcovParams p) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     constexpr int ld = NB * 8 + 4;
@@ -244,6 +253,11 @@ __global__ void __launch_bounds__(KC_THREADS, 1) kcov_gemm_kernel(const __grid_c
                     if (clock64() - t0 > KC_SPIN_LIMIT) { window_on = false; break; }
                 }
             }
+        }
+        if (PREF) {
+            int64_t ktp = kt + p.pref_ahead;
+            if (ktp >= nkt) ktp -= nkt;
+            if (p.pref_ahead < nkt) bulk_prefetch_l2(p.X + ktp * KC_BK * p.ld, KC_BK * ld * 8);
         }
         mbar_wait(&empty[s], ph ^ 1u);
         double* xs = smem + (size_t)s * stage_doubles;
@@ -463,7 +477,7 @@ __global__ void __launch_bounds__(KC_THREADS, 1) kcov_gemm_kernel(const __grid_c
     }
 }
 
-template <int NB, int KIND, int DIM, int PACE = 1>
+template <int NB, int KIND, int DIM, int PACE = 1, int PREF = 0>
 static void launch_kcov(gsi_ctx* ctx, const KcovParams& p0) {
     KcovParams p = p0;
     const int ld = NB * 8 + 4;
@@ -474,7 +488,7 @@ static void launch_kcov(gsi_ctx* ctx, const KcovParams& p0) {
     if (stages < 2) stages = 2;
     p.stages = stages;
     const size_t smem = stages * stage_bytes + a_bytes + (2 * stages + 4) * sizeof(uint64_t) + 64 * sizeof(double);
-    auto kfn = kcov_gemm_kernel<NB, KIND, DIM, PACE>;
+    auto kfn = kcov_gemm_kernel<NB, KIND, DIM, PACE, PREF>;
     GSI_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int occ = 0;
     GSI_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kfn, KC_THREADS, smem));
@@ -483,6 +497,7 @@ static void launch_kcov(gsi_ctx* ctx, const KcovParams& p0) {
     int64_t grid = (int64_t)ctx->num_sms * occ;
     if (grid > total_rg) grid = total_rg;
     if (grid < 1) grid = 1;
+    p.pref_ahead = ctx->kcov_prefetch > 0 ? ctx->kcov_prefetch : 0;
     p.win_epochs = ctx->kcov_window > 0 ? ctx->kcov_window : 0;
     p.epoch_shift = ctx->kcov_epoch_shift;
     p.sync_cnt = nullptr;
@@ -510,6 +525,11 @@ static void dispatch_dim(gsi_ctx* ctx, const KcovParams& p, int dim) {
     if (KIND == KC_KIND_TABLE && ctx->kcov_pace > 1) {          // experimental paced X fetch (4 chunks)
         if (dim <= 2) launch_kcov<NB, KIND, 2, (KIND == KC_KIND_TABLE ? 4 : 1)>(ctx, p);
         else launch_kcov<NB, KIND, 3, (KIND == KC_KIND_TABLE ? 4 : 1)>(ctx, p);
+        return;
+    }
+    if (KIND == KC_KIND_TABLE && ctx->kcov_prefetch > 0) {      // experimental L2 prefetch ahead of the sweep
+        if (dim <= 2) launch_kcov<NB, KIND, 2, 1, (KIND == KC_KIND_TABLE ? 1 : 0)>(ctx, p);
+        else launch_kcov<NB, KIND, 3, 1, (KIND == KC_KIND_TABLE ? 1 : 0)>(ctx, p);
         return;
     }
     if (dim <= 2) launch_kcov<NB, KIND, 2>(ctx, p);

@@ -68,6 +68,11 @@ __device__ __forceinline__ void bulk_g2s_hint(void* smem_dst, const void* gmem_s
         :: "r"(smem_u32(smem_dst)), "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar)), "l"(policy) : "memory");
 }
 
+// Bulk prefetch of a contiguous global range into L2 (no shared-memory destination, no barrier).
+__device__ __forceinline__ void bulk_prefetch_l2(const void* gmem_src, uint32_t bytes) {
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" :: "l"(gmem_src), "r"(bytes) : "memory");
+}
+
 // 2-D tiled TMA load: box at element coordinates (c0 = innermost, c1).
 __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* map, int c0, int c1,
                                             uint64_t* bar) {

@@ -119,6 +119,8 @@ int32_t gsi_ctx_phase_timing(gsi_ctx* ctx, double* ms_out8, int32_t reset);
  *                        parallel (still deterministic) reduction of the per-CTA partial sums
  *   "kcov.pace"          EXPERIMENTAL, default 0: > 1 fetches each X tile of the structured-grid
  *                        product kernel as 4 bulk copies spread over the k-steps (burst probe)
+ *   "kcov.prefetch"      EXPERIMENTAL, default 0: > 0 adds an L2 bulk prefetch of the X tile this
+ *                        many k-tiles ahead of each CTA's sweep (structured-grid product kernel)
  * The environment variables GSI_SWEEP="groups,div,hint[,window[,epoch_shift]]" and
  * GSI_OPTIONS="name=value,name=value" set the same knobs at context creation.         */
 int32_t gsi_ctx_set_option(gsi_ctx* ctx, const char* name, int64_t value);

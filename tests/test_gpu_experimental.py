@@ -135,3 +135,21 @@ def test_kcov_paced_fetch_is_bit_identical(gsi):
     coords = oracle.grid_coords(grid)
     rows = np.random.default_rng(6).choice(n, 100, replace=False)
     assert relerr(Y1[rows], oracle.kernel_cov_dense(0, coords, ell, rows=rows) @ X) < 1e-12
+
+
+def test_kcov_l2_prefetch_is_bit_identical(gsi):
+    """"kcov.prefetch": an extra L2 bulk prefetch ahead of each CTA's sweep moves no result."""
+    ctx = gsi.default_context()
+    grid, ell, l = (110, 109), [7.0, 5.0], 24
+    n = grid[0] * grid[1]
+    X = np.random.default_rng(5).standard_normal((n, l))
+    op = gsi.GridKernelCovMatrix("gaussian", grid, ell)
+    saved = ctx.get_option("kcov.prefetch")
+    try:
+        ctx.set_option("kcov.prefetch", 0)
+        Y0 = op @ X
+        for ahead in (1, 3, 400):              # 400 > number of k-tiles: the prefetch is skipped
+            ctx.set_option("kcov.prefetch", ahead)
+            assert np.array_equal(op @ X, Y0)
+    finally:
+        ctx.set_option("kcov.prefetch", saved)

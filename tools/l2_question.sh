@@ -23,3 +23,10 @@ echo "arith probe rc=$?"; tail -3 gpurun_out/sweep_probe_arith.log
 timeout 60 python tools/sweep_probe.py --set coherent --only 0 1 --pace 4 --reps 2 \
     --out gpurun_out/sweep_probe_paced.json > gpurun_out/sweep_probe_paced.log 2>&1
 echo "paced probe rc=$?"; tail -3 gpurun_out/sweep_probe_paced.log
+# The cleanest test (and a possible win: 5 % of the default launch's warp samples wait for X tiles): default
+# schedule, but every shared-memory fill made an L2 hit by a bulk prefetch 2 / 4 k-tiles ahead.
+for AHEAD in 2 4; do
+    timeout 40 python tools/sweep_probe.py --set coherent --only 0 --prefetch $AHEAD --reps 2 \
+        --out gpurun_out/sweep_probe_pref$AHEAD.json > gpurun_out/sweep_probe_pref$AHEAD.log 2>&1
+    echo "prefetch $AHEAD rc=$?"; tail -1 gpurun_out/sweep_probe_pref$AHEAD.log
+done

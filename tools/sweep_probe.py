@@ -64,6 +64,7 @@ def main():
     ap.add_argument("--no-warm", action="store_true")
     ap.add_argument("--control", action="store_true", help="also time an L2-resident problem (X = 50 MB)")
     ap.add_argument("--pace", type=int, default=0, help="kcov.pace (experimental paced X fetch)")
+    ap.add_argument("--prefetch", type=int, default=0, help="kcov.prefetch (experimental L2 prefetch, k-tiles ahead)")
     ap.add_argument("--generation", default="table", choices=["table", "arithmetic"],
                     help="kernel values from the lattice table (default) or from coordinates (no table look-ups "
                          "on the L2 return path: separates the two suspects of the L2-served-stream penalty)")
@@ -86,6 +87,7 @@ def main():
     Y = gsi.DeviceMatrix(ctx, n, l)
     lib = ctx._lib
     ctx.set_option("kcov.pace", args.pace)
+    ctx.set_option("kcov.prefetch", args.prefetch)
 
     def apply():
         gsi._lib.check(lib.gsi_op_apply(op._h, 0, X._h, Y._h))
@@ -147,7 +149,7 @@ def main():
             print("control", json.dumps(control[-1]), flush=True)
     os.makedirs(os.path.dirname(args.out), exist_ok=True)
     with open(args.out, "w") as f:
-        json.dump({"workload": desc, "n": n, "l": l, "generation": args.generation, "pace": args.pace, "schedules": rows,
+        json.dump({"workload": desc, "n": n, "l": l, "generation": args.generation, "pace": args.pace, "prefetch": args.prefetch, "schedules": rows,
                    "l2fit_control": control}, f, indent=1)
 
 
