@@ -145,19 +145,12 @@ static void gather_rows(gsi_op* op, const gsi_buf* loc, gsi_buf* full) {
 
 static bool op_symmetric(const gsi_op* op) { return op->type != OP_DENSE; }
 
-// In-place normalisation of a (possibly row-sharded) iterate.
-static void normalise_lu(gsi_op* op, gsi_buf* Y, bool sharded) {
+// In-place LU normalisation of an iterate all of whose rows are on this device.
+static void normalise_lu(gsi_op* op, gsi_buf* Y) {
     gsi_ctx* ctx = op->ctx;
     phase_begin(ctx);
     struct End { gsi_ctx* c; ~End() { try { phase_end(c, PH_LU); } catch (...) {} } } end_{ctx};
-    if (sharded && ctx->world > 1) {
-        lu_L_inplace(ctx, Y, op->row0, op->m, op->part.data());
-    } else {
-        const int saved = ctx->world;
-        ctx->world = 1;                       // replicated iterate: every rank factors all rows
-        try { lu_L_inplace(ctx, Y, 0, Y->rows, nullptr); } catch (...) { ctx->world = saved; throw; }
-        ctx->world = saved;
-    }
+    lu_L_inplace(ctx, Y);
 }
 
 // TSQR: local Householder QR, all-gather of the R factors, redundant QR of the stack,
@@ -203,7 +196,7 @@ void tsqr_thinQ(gsi_op* op, gsi_buf* Y, bool sharded, double* Rdev) {
     BufPtr tmp = make_buf(ctx, GSI_LAYOUT_TALL, Yl->rows, l);
     tall_times_small(ctx, Yl, qt.get(), tmp.get());
     GSI_CUDA(cudaMemcpyAsync(Y->d, tmp->d, (size_t)Y->rows * Y->ld * 8, cudaMemcpyDeviceToDevice, ctx->stream));
-    GSI_CUDA(cudaStreamSynchronize(ctx->stream));
+    // no host synchronisation: the temporaries go back to the stream-ordered pool of this context
 }
 
 // One product step of the iteration.  `cur` holds the current iterate in distribution
@@ -213,10 +206,10 @@ struct Iterate {
     bool sharded = false;     // true: this rank holds rows [row0, row0+mloc) only
 };
 
-// EXPERIMENTAL (option "lu.replicate", default off): the next product needs the whole iterate on
-// every rank anyway, so gather it BEFORE the LU and let every rank factor all rows redundantly
-// (deterministic kernels: identical factors everywhere, identical to the single-GPU result)
-// instead of exchanging pivot candidates per column.  Pays off only with a fast local LU.
+// Multi-GPU LU normalisation: the next product needs the whole iterate on every rank anyway, so it
+// is gathered BEFORE the LU and every rank factors all rows redundantly (deterministic kernels:
+// identical factors everywhere, identical to the single-GPU result) -- no per-column pivot
+// exchange.  The gathered, normalised iterate is then the next product's operand as it stands.
 static void replicate(gsi_op* op, Iterate& it) {
     gsi_ctx* ctx = op->ctx;
     if (!(it.sharded && ctx->world > 1)) return;
@@ -228,8 +221,8 @@ static void replicate(gsi_op* op, Iterate& it) {
 
 static void normalise(gsi_op* op, Iterate& it, int normaliser) {
     if (normaliser == GSI_NORMALISER_LU_REF) {
-        if (op->ctx->lu_replicate && op->type != OP_DENSE) replicate(op, it);
-        normalise_lu(op, it.buf.get(), it.sharded);
+        replicate(op, it);
+        normalise_lu(op, it.buf.get());
     } else {
         tsqr_thinQ(op, it.buf.get(), it.sharded, nullptr);
     }
@@ -272,6 +265,7 @@ static Iterate rangefinder_fixed_impl(gsi_op* op, const gsi_buf* Omega, int64_t 
     GSI_REQUIRE(l <= op->n && l <= op->m, GSI_ERR_UNSUPPORTED, "l must not exceed min(size(A))");
     BufPtr full_scratch;
     Iterate cur;
+    lu_reset_flag(ctx);
     {
         // Y = A * Omega                                         (reference :55)
         Iterate om;
@@ -311,7 +305,8 @@ static void deliver(gsi_op* op, Iterate& res, gsi_buf* out) {
                                      cudaMemcpyDeviceToDevice, ctx->stream));
         else throw Error(GSI_ERR_DIMENSION_MISMATCH, "output buffer: wrong row count");
     }
-    GSI_CUDA(cudaStreamSynchronize(ctx->stream));
+    lu_check_singular(ctx);          // the one host synchronisation of the algorithm (SingularException of any LU)
+    svd_check(ctx);                  // ... and the Jacobi convergence verdict (stream already idle)
 }
 
 void rangefinder_fixed(gsi_op* op, const gsi_buf* Omega, int64_t q, int normaliser, gsi_buf* Q_out) {
@@ -348,7 +343,7 @@ void randsvd(gsi_op* op, const gsi_buf* Omega, int64_t K, int64_t p, int64_t q, 
     double* sigma = small + (size_t)3 * l * l;
     tsqr_thinQ(op, Bt.buf.get(), Bt.sharded, R);
     phase_begin(ctx);
-    svd_small(ctx, R, l, U, sigma);
+    svd_small(ctx, R, l, U, sigma, /*defer_check=*/true);
     phase_end(ctx, PH_SVD);
     // Z = V * Diagonal(sqrt.([S[1:K]; zeros(p)]))                        (:87-88)
     scale_cols_kernel<<<(l * l + 255) / 256, 256, 0, ctx->stream>>>(U, sigma, l, (int)K, Usc);

@@ -95,11 +95,8 @@ static void set_option_impl(gsi_ctx* ctx, const std::string& n, int64_t value) {
     else if (n == "kcov.window") ctx->kcov_window = v;
     else if (n == "kcov.epoch_shift") ctx->kcov_epoch_shift = v;
     else if (n == "svd.fused") ctx->svd_fused = v != 0;
-    else if (n == "lu.fused") ctx->lu_fused = v != 0;
-    else if (n == "lu.replicate") ctx->lu_replicate = v != 0;
-    else if (n == "qr.fast_house") ctx->qr_fast_house = v != 0;
-    else if (n == "kcov.pace") ctx->kcov_pace = v;
-    else if (n == "kcov.prefetch") ctx->kcov_prefetch = v < 0 ? 0 : (v > 4096 ? 4096 : v);
+    else if (n == "lu.panel") ctx->lu_panel = v != 0;
+    else if (n == "qr.panel") ctx->qr_panel = v != 0;
     else throw Error(GSI_ERR_INVALID_ARGUMENT, "unknown option '" + n + "'");
     try {
         validate_kcov_options(ctx);
@@ -147,6 +144,8 @@ GSI_API int32_t gsi_comm_unique_id(void* out128) {
     });
 }
 
+static void ctx_really_destroy(gsi_ctx* ctx);
+
 GSI_API int32_t gsi_ctx_create(int32_t device, int32_t rank, int32_t world, const void* unique_id128, gsi_ctx** out) {
     return guarded([&] {
         GSI_REQUIRE(out != nullptr, GSI_ERR_INVALID_ARGUMENT, "null output");
@@ -161,11 +160,12 @@ GSI_API int32_t gsi_ctx_create(int32_t device, int32_t rank, int32_t world, cons
         GSI_REQUIRE(device >= 0 && device < ndev, GSI_ERR_INVALID_ARGUMENT, "device index out of range");
         cudaDeviceProp prop;
         GSI_CUDA(cudaGetDeviceProperties(&prop, device));
-        if (prop.major != 10)
+        if (prop.major != 10 || prop.minor != 0)      // sm_100a SASS only: no PTX, not even other 10.x parts can run it
             throw Error(GSI_ERR_NO_DEVICE, std::string("device '") + prop.name + "' is sm_" + std::to_string(prop.major) +
                                                std::to_string(prop.minor) + "; gsi_b200 is built for sm_100a only");
         GSI_CUDA(cudaSetDevice(device));
-        std::unique_ptr<gsi_ctx> ctx(new gsi_ctx());
+        // failure paths release whatever was created so far (stream, scratch, events, NCCL communicator)
+        std::unique_ptr<gsi_ctx, void (*)(gsi_ctx*)> ctx(new gsi_ctx(), ctx_really_destroy);
         ctx->device = device; ctx->rank = rank; ctx->world = world;
         ctx->num_sms = prop.multiProcessorCount;
         GSI_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
@@ -189,7 +189,7 @@ GSI_API int32_t gsi_ctx_create(int32_t device, int32_t rank, int32_t world, cons
 
 static void ctx_really_destroy(gsi_ctx* ctx) {
     cudaSetDevice(ctx->device);
-    cudaStreamSynchronize(ctx->stream);
+    if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     comm_destroy(ctx);
     pool_release(ctx);
     if (ctx->scratch) cudaFree(ctx->scratch);
@@ -252,11 +252,8 @@ GSI_API int32_t gsi_ctx_get_option(gsi_ctx* ctx, const char* name, int64_t* valu
         else if (n == "kcov.window") *value_out = ctx->kcov_window;
         else if (n == "kcov.epoch_shift") *value_out = ctx->kcov_epoch_shift;
         else if (n == "svd.fused") *value_out = ctx->svd_fused;
-        else if (n == "lu.fused") *value_out = ctx->lu_fused;
-        else if (n == "lu.replicate") *value_out = ctx->lu_replicate;
-        else if (n == "qr.fast_house") *value_out = ctx->qr_fast_house;
-        else if (n == "kcov.pace") *value_out = ctx->kcov_pace;
-        else if (n == "kcov.prefetch") *value_out = ctx->kcov_prefetch;
+        else if (n == "lu.panel") *value_out = ctx->lu_panel;
+        else if (n == "qr.panel") *value_out = ctx->qr_panel;
         else throw Error(GSI_ERR_INVALID_ARGUMENT, "unknown option '" + n + "'");
     });
 }
@@ -400,6 +397,17 @@ static void set_partition(gsi_op* op) {
                 "row partition must be contiguous and cover all rows");
 }
 
+// failure paths of the operator constructors: device arrays of a half-built operator are released
+struct OpAbort {
+    void operator()(gsi_op* op) const {
+        if (!op) return;
+        if (op->ucoords) cudaFree(op->ucoords);
+        if (op->table) cudaFree(op->table);
+        if (op->lattice) cudaFree(op->lattice);
+        delete op;
+    }
+};
+
 GSI_API int32_t gsi_op_dense(gsi_ctx* ctx, gsi_buf* A_local, int64_t row0, int64_t m_global, gsi_op** out) {
     return guarded([&] {
         use(ctx);
@@ -455,7 +463,7 @@ GSI_API int32_t gsi_op_kernelcov(gsi_ctx* ctx, int32_t kind, int32_t d, int64_t 
         GSI_REQUIRE(kind >= 0 && kind <= 2, GSI_ERR_INVALID_ARGUMENT, "kernelcov: unknown kernel kind");
         GSI_REQUIRE(n >= 1 && row0 >= 0 && mloc >= 0 && row0 + mloc <= n, GSI_ERR_INVALID_ARGUMENT, "kernelcov: bad row block");
         for (int k = 0; k < d; ++k) GSI_REQUIRE(ell[k] > 0.0, GSI_ERR_INVALID_ARGUMENT, "kernelcov: length scales must be positive");
-        std::unique_ptr<gsi_op> op(new gsi_op());
+        std::unique_ptr<gsi_op, OpAbort> op(new gsi_op());
         op->ctx = ctx; op->type = OP_KERNELCOV; op->kind = kind; op->dim = d;
         op->m = op->n = n; op->row0 = row0; op->mloc = mloc;
         op->sigma2 = sigma2; op->nugget = nugget; op->beta = beta;
@@ -496,7 +504,7 @@ GSI_API int32_t gsi_op_kernelcov_grid(gsi_ctx* ctx, int32_t kind, int32_t d, con
         }
         GSI_REQUIRE(n < ((int64_t)1 << 31), GSI_ERR_UNSUPPORTED, "kernelcov_grid: more than 2^31 points");
         GSI_REQUIRE(row0 >= 0 && mloc >= 0 && row0 + mloc <= n, GSI_ERR_INVALID_ARGUMENT, "kernelcov_grid: bad row block");
-        std::unique_ptr<gsi_op> op(new gsi_op());
+        std::unique_ptr<gsi_op, OpAbort> op(new gsi_op());
         op->ctx = ctx; op->type = OP_KERNELCOV; op->kind = kind; op->dim = d;
         op->m = op->n = n; op->row0 = row0; op->mloc = mloc;
         op->sigma2 = sigma2; op->nugget = nugget; op->beta = beta;
@@ -573,10 +581,9 @@ GSI_API int32_t gsi_lu_L(gsi_ctx* ctx, gsi_buf* Y) {
     return guarded([&] {
         use(ctx);
         GSI_REQUIRE(Y != nullptr, GSI_ERR_INVALID_ARGUMENT, "null buffer");
-        const int saved = ctx->world;
-        ctx->world = 1;
-        try { lu_L_inplace(ctx, Y, 0, Y->rows, nullptr); } catch (...) { ctx->world = saved; throw; }
-        ctx->world = saved;
+        lu_reset_flag(ctx);
+        lu_L_inplace(ctx, Y);
+        lu_check_singular(ctx);
     });
 }
 

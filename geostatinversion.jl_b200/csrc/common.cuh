@@ -92,12 +92,12 @@ struct gsi_ctx {
     // small Jacobi SVD: all sweeps in one cluster launch (svd.cu; gsi_ctx_set_option "svd.fused")
     int svd_fused = 1;
     int* jflags = nullptr;               // [60] rotations per sweep, [60] sweeps used
-    // EXPERIMENTAL, default off, not yet run on hardware (gsi_ctx_set_option "lu.fused" / "lu.replicate"):
-    int lu_fused = 0;                    // panel column steps in one cooperative launch (rows all local)
-    int lu_replicate = 0;                // multi-GPU: gather the iterate and factor it redundantly on every rank
-    int qr_fast_house = 0;               // Householder-scalar kernel with a parallel reduction of the partials
-    int kcov_pace = 0;                   // > 1: X tiles of the structured-grid product kernel fetched in 4 paced chunks
-    int kcov_prefetch = 0;               // > 0: L2 bulk prefetch of the X tile this many k-tiles ahead of the sweep
+    bool svd_pending = false;            // a single-launch Jacobi run whose convergence flag has not been read yet
+    // factorisation drivers (lu.cu / qr.cu; gsi_ctx_set_option "lu.panel" / "qr.panel"): 1 = one cooperative
+    // launch per 16-column panel with the panel rows resident in shared memory (default), 0 = one or two
+    // launches per column (the first round's scheme, kept as the independent implementation to test against)
+    int lu_panel = 1;
+    int qr_panel = 1;
 };
 
 struct gsi_buf {
@@ -156,15 +156,19 @@ void dense_apply(gsi_ctx*, const gsi_buf* A, int trans, const gsi_buf* X, gsi_bu
 void tall_window_update(gsi_ctx*, const double* Pd, int64_t ldp, int64_t rows, int64_t kdim, const gsi_buf* X,
                         double* Wd, int64_t ldw, double alpha);
 // ---- lu.cu : in place, returns unit-lower-trapezoidal L in LAPACK row order
-void lu_L_inplace(gsi_ctx*, gsi_buf* Y, int64_t row0_global, int64_t n_global, const int64_t* part_row0 /* world+1 */);
+// (all rows of Y on this device; enqueue only -- the zero-pivot flag is read by lu_check_singular)
+void lu_L_inplace(gsi_ctx*, gsi_buf* Y);
+void lu_reset_flag(gsi_ctx*);
+void lu_check_singular(gsi_ctx*);      // synchronises; throws GSI_ERR_SINGULAR if an LU since the last reset met a zero pivot
 // ---- qr.cu : in place thin Q; R (l x l, column-major, device) optional
 void qr_thinQ_inplace(gsi_ctx*, gsi_buf* Y, double* Rdev /* l*l or null */);
 // ---- svd.cu : one-sided Jacobi on l x l column-major device matrix M (overwritten with U),
 //      sigma (device, l) sorted descending, columns of U permuted accordingly
-void svd_small(gsi_ctx*, double* M, int l, double* U, double* sigma);
+void svd_small(gsi_ctx*, double* M, int l, double* U, double* sigma, bool defer_check = false);
+void svd_check(gsi_ctx*);               // verdict of a deferred convergence check (synchronises)
 //      the sweeps alone, on the first rows_dot rows of ncols columns (pitch ld); rotations are applied
 //      to all rows_all rows (rows below rows_dot accumulate the right singular vectors)
-void jacobi_sweeps(gsi_ctx*, double* M, int64_t ld, int rows_dot, int rows_all, int ncols);
+void jacobi_sweeps(gsi_ctx*, double* M, int64_t ld, int rows_dot, int rows_all, int ncols, bool defer_check = false);
 // ---- comm.cu
 void comm_allgather(gsi_ctx*, const void* send, void* recv, size_t bytes_per_rank);
 void comm_allreduce_sum(gsi_ctx*, double* buf, size_t count);

@@ -43,7 +43,7 @@ struct KcovParams {
     const double* table;   // k(r2) for every lattice offset: table[dx + nx*(dy + ny*dz)]
     int nx, ny;
     int sweep_groups, sweep_div, l2_hint;   // k-sweep de-synchronisation (power-of-two groups, spread = groups/div of X)
-    int pref_ahead;                         // PREF variant: L2 prefetch distance in k-tiles (sits in what was padding)
+    int pad0;
     unsigned int* sync_cnt;                 // sweep window: arrivals per epoch (zeroed before the launch)
     int win_epochs, epoch_shift;            // a CTA runs at most win_epochs epochs of 2^epoch_shift k-tiles ahead of the slowest
     int64_t n;             // columns of C (= rows of X)
@@ -101,7 +101,9 @@ __device__ __forceinline__ double fast_exp_neg(double y, const double* __restric
     const int e = k >> 6;                                  // floor(k / 64) <= 0
     const int hi = __double2hiint(v) + (e << 20);
     const double res = __hiloint2double(hi, __double2loint(v));
-    return e < -1000 ? 0.0 : res;
+    // y >= 1024 (hi word >= 0x40900000; also inf/NaN): k would wrap for y >~ 2.3e7 -- flush by the
+    // integer compare on y itself (no FP64-pipe instruction)
+    return (e < -1000 || __double2hiint(y) >= 0x40900000) ? 0.0 : res;
 }
 
 // sqrt(x) for x > 0 (callers add 1e-300 so the diagonal r2 = 0 stays finite): hardware
@@ -133,19 +135,12 @@ __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
     asm volatile("bar.sync %0, %1;" :: "r"(id), "r"(nthreads) : "memory");
 }
 
-// EXPERIMENTAL variants (structured-grid operator only, not yet run on hardware; the default
-// instantiations PACE = 1, PREF = 0 compile to the same SASS as before they were added):
-//   PACE > 1 (option "kcov.pace"): the X tile of the next k-tile is fetched as PACE bulk copies
-//     issued 8/PACE k-steps apart instead of one 56 KB copy -- a probe for the L2-served-stream
-//     penalty (does the burst with which an L2 hit lands in shared memory cost the MMA warps
-//     their fragment loads?);
-//   PREF = 1 (option "kcov.prefetch" = tiles ahead): the producer also issues an L2 bulk prefetch
-//     of the X tile `pref_ahead` k-tiles further down its sweep.  Shared memory has room for one
-//     tile of look-ahead only (3 stages of 56 KB), and 5 % of the warp samples of the default
-//     launch wait on the `full` barrier, i.e. on HBM latency tails; with the prefetch the copy
-//     into shared memory is an L2 hit.  It doubles as the cleanest test of the penalty: default
-//     schedule, every fill an L2 hit.
-template <int NB, int KIND, int DIM, int PACE = 1, int PREF = 0>
+// (Two probes of the first round -- the X tile fetched as four paced bulk copies, and an L2 bulk
+// prefetch a few k-tiles ahead of every CTA's sweep -- were run on hardware in round 2
+// (profiles/r02/l2_question.md): both bit-identical, the paced fetch 19 % slower, the prefetch
+// within 0.1 % of the default although it turns every shared-memory fill into an L2 hit.  So an
+// L2-served X stream is not slower as such; both variants were removed.)
+template <int NB, int KIND, int DIM>
 __global__ void __launch_bounds__(KC_THREADS, 1) kcov_gemm_kernel(const __grid_constant__ KcovParams p) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     constexpr int ld = NB * 8 + 4;
@@ -254,17 +249,11 @@ __global__ void __launch_bounds__(KC_THREADS, 1) kcov_gemm_kernel(const __grid_c
                 }
             }
         }
-        if (PREF) {
-            int64_t ktp = kt + p.pref_ahead;
-            if (ktp >= nkt) ktp -= nkt;
-            if (p.pref_ahead < nkt) bulk_prefetch_l2(p.X + ktp * KC_BK * p.ld, KC_BK * ld * 8);
-        }
         mbar_wait(&empty[s], ph ^ 1u);
         double* xs = smem + (size_t)s * stage_doubles;
         double* us = xs + KC_BK * ld;
         mbar_expect_tx(&full[s], stage_bytes);
-        if (PACE > 1) bulk_g2s(xs, p.X + kt * KC_BK * p.ld, (KC_BK / PACE) * ld * 8, &full[s]);     // chunk 0
-        else if (p.l2_hint) bulk_g2s_hint(xs, p.X + kt * KC_BK * p.ld, KC_BK * ld * 8, &full[s], xpolicy);
+        if (p.l2_hint) bulk_g2s_hint(xs, p.X + kt * KC_BK * p.ld, KC_BK * ld * 8, &full[s], xpolicy);
         else bulk_g2s(xs, p.X + kt * KC_BK * p.ld, KC_BK * ld * 8, &full[s]);
         const int64_t ktn = (kt + 1 == nkt) ? 0 : kt + 1;      // coordinates of the NEXT k-tile ride along
         if (KIND == KC_KIND_TABLE) {
@@ -276,19 +265,9 @@ __global__ void __launch_bounds__(KC_THREADS, 1) kcov_gemm_kernel(const __grid_c
                 bulk_g2s(us + k * KC_BK, p.u + k * p.n_pad + ktn * KC_BK, KC_BK * 8, &full[s]);
         }
     };
-    // chunk c (1 .. PACE-1) of the X tile whose chunk 0 `produce(nxt)` has already issued
-    auto produce_chunk = [&](int64_t nxt, int c) {
-        const int s = (int)(nxt % nstages);
-        int64_t kt = nxt % nkt + kt0;
-        if (kt >= nkt) kt -= nkt;
-        constexpr int chunk = (KC_BK / (PACE > 1 ? PACE : 1)) * ld;          // doubles
-        bulk_g2s(smem + (size_t)s * stage_doubles + c * chunk, p.X + kt * KC_BK * p.ld + c * chunk, chunk * 8, &full[s]);
-    };
     if (tid == 0) {
         for (int64_t i = 0; i < lookahead && i < total_it; ++i) {
             produce(i);
-            if (PACE > 1)
-                for (int c = 1; c < PACE; ++c) produce_chunk(i, c);
         }
     }
 
@@ -410,9 +389,6 @@ __global__ void __launch_bounds__(KC_THREADS, 1) kcov_gemm_kernel(const __grid_c
             const double* arow1 = arow0 + 8 * KC_AP;
 #pragma unroll
             for (int ks = 0; ks < KC_BK / 4; ++ks) {
-                if (PACE > 1 && tid == 0 && ks > 0 && ks % (KC_BK / 4 / (PACE > 1 ? PACE : 1)) == 0 &&
-                    it + lookahead < total_it)
-                    produce_chunk(it + lookahead, ks / (KC_BK / 4 / (PACE > 1 ? PACE : 1)));
                 // one kernel value of the NEXT k-tile every second k-step: a single exp chain
                 // is live at a time and its DFMAs interleave with this step's DMMAs
                 if (KIND != KC_KIND_TABLE && (ks & 1) == 0 && gen_next) {
@@ -477,7 +453,7 @@ __global__ void __launch_bounds__(KC_THREADS, 1) kcov_gemm_kernel(const __grid_c
     }
 }
 
-template <int NB, int KIND, int DIM, int PACE = 1, int PREF = 0>
+template <int NB, int KIND, int DIM>
 static void launch_kcov(gsi_ctx* ctx, const KcovParams& p0) {
     KcovParams p = p0;
     const int ld = NB * 8 + 4;
@@ -488,7 +464,7 @@ static void launch_kcov(gsi_ctx* ctx, const KcovParams& p0) {
     if (stages < 2) stages = 2;
     p.stages = stages;
     const size_t smem = stages * stage_bytes + a_bytes + (2 * stages + 4) * sizeof(uint64_t) + 64 * sizeof(double);
-    auto kfn = kcov_gemm_kernel<NB, KIND, DIM, PACE, PREF>;
+    auto kfn = kcov_gemm_kernel<NB, KIND, DIM>;
     GSI_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int occ = 0;
     GSI_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kfn, KC_THREADS, smem));
@@ -497,7 +473,7 @@ static void launch_kcov(gsi_ctx* ctx, const KcovParams& p0) {
     int64_t grid = (int64_t)ctx->num_sms * occ;
     if (grid > total_rg) grid = total_rg;
     if (grid < 1) grid = 1;
-    p.pref_ahead = ctx->kcov_prefetch > 0 ? ctx->kcov_prefetch : 0;
+    p.pad0 = 0;
     p.win_epochs = ctx->kcov_window > 0 ? ctx->kcov_window : 0;
     p.epoch_shift = ctx->kcov_epoch_shift;
     p.sync_cnt = nullptr;
@@ -522,16 +498,6 @@ static void launch_kcov(gsi_ctx* ctx, const KcovParams& p0) {
 
 template <int NB, int KIND>
 static void dispatch_dim(gsi_ctx* ctx, const KcovParams& p, int dim) {
-    if (KIND == KC_KIND_TABLE && ctx->kcov_pace > 1) {          // experimental paced X fetch (4 chunks)
-        if (dim <= 2) launch_kcov<NB, KIND, 2, (KIND == KC_KIND_TABLE ? 4 : 1)>(ctx, p);
-        else launch_kcov<NB, KIND, 3, (KIND == KC_KIND_TABLE ? 4 : 1)>(ctx, p);
-        return;
-    }
-    if (KIND == KC_KIND_TABLE && ctx->kcov_prefetch > 0) {      // experimental L2 prefetch ahead of the sweep
-        if (dim <= 2) launch_kcov<NB, KIND, 2, 1, (KIND == KC_KIND_TABLE ? 1 : 0)>(ctx, p);
-        else launch_kcov<NB, KIND, 3, 1, (KIND == KC_KIND_TABLE ? 1 : 0)>(ctx, p);
-        return;
-    }
     if (dim <= 2) launch_kcov<NB, KIND, 2>(ctx, p);
     else launch_kcov<NB, KIND, 3>(ctx, p);
 }

@@ -4,13 +4,17 @@
 // precedes the small SVD (`svd(B)`, :86).
 //
 // Blocked (compact-WY) algorithm with panels of QB = 16 columns, LAPACK dgeqrt/dorgqr style:
-//   panel factorisation  column by column with dgeqr2/dlarfg reflectors, but touching only
-//                        the n x 16 panel (L2-resident): per column one single-CTA kernel
-//                        (Householder scalars from the dot products the previous pass
-//                        accumulated, row-k update) and one grid pass (scale column k to v,
-//                        apply the reflector to the panel, and -- fused -- accumulate the
-//                        next column's dot products: 4 lanes per row, warp-shuffle
-//                        broadcast/reduction);
+//   panel factorisation  column by column with dgeqr2/dlarfg reflectors, touching only the
+//                        n x 16 panel.  Default driver (option "qr.panel" = 1): ONE cooperative
+//                        launch per panel, qr_panel_kernel -- every CTA keeps its rows of the
+//                        panel in SHARED MEMORY for all 16 column steps; a step is: publish the
+//                        CTA's partial dot products (column k against the panel) -> one grid
+//                        barrier -> every CTA reduces the partials in the same fixed order and
+//                        derives the Householder scalars redundantly -> applies the reflector to
+//                        its rows and accumulates the next column's dot products (4 lanes per
+//                        row, warp-shuffle reductions).  Second driver ("qr.panel" = 0, the
+//                        first round's scheme): per column one single-CTA kernel (scalars) and
+//                        one grid pass (update), the panel served from L2;
 //   T factor             G = V'V by the DMMA Gram kernel + dlarft recurrence (16 x 16);
 //   trailing update      W = V'Y2 (DMMA Gram kernel, split over row chunks, deterministic
 //                        two-stage reduction), W <- T'W, Y2 -= V W on the dense DMMA GEMM
@@ -22,6 +26,9 @@
 #include "algos.h"
 #include "ptx.cuh"
 #include "nb_list.h"
+#include <cooperative_groups.h>
+
+namespace cg = cooperative_groups;
 
 namespace gsi {
 
@@ -73,52 +80,10 @@ qr_panel_dots_kernel(const double* __restrict__ Y, int64_t ld, int64_t n, int ps
 }
 
 // Householder scalars of column k (dlarfg) + row-k update inside the panel.  tw[jj] = tau*w_j.
+// The per-CTA partials are reduced by all 256 threads (16 slices per column, combined in a
+// fixed order): deterministic, and 20 us per column faster than 16 threads walking them.
 __global__ void __launch_bounds__(QP_THREADS)
 qr_house_kernel(double* __restrict__ Y, int64_t ld, int ps, int pe, int k, const double* __restrict__ partial,
-                int nparts, double* __restrict__ tw, double* __restrict__ taus, QrScal* __restrict__ scal) {
-    __shared__ double s_g[QB];
-    __shared__ double s_tau, s_scale;
-    if (threadIdx.x < QB) {
-        double s = 0.0;
-        for (int b = 0; b < nparts; ++b) s += partial[(size_t)b * QB + threadIdx.x];
-        s_g[threadIdx.x] = s;
-    }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        const double alpha = Y[(int64_t)k * ld + k];
-        const double xnorm2 = s_g[k - ps];
-        double tau = 0.0, scale = 0.0, beta = alpha;
-        if (xnorm2 > 0.0) {
-            const double nrm = sqrt(alpha * alpha + xnorm2);
-            beta = (alpha >= 0.0) ? -nrm : nrm;
-            tau = (beta - alpha) / beta;
-            scale = 1.0 / (alpha - beta);
-        }
-        Y[(int64_t)k * ld + k] = beta;
-        taus[k] = tau;
-        s_tau = tau; s_scale = scale;
-        scal->tau = tau; scal->scale = scale; scal->beta = beta;
-    }
-    __syncthreads();
-    const double tau = s_tau, scale = s_scale;
-    const int j = k + 1 + threadIdx.x;
-    if (j < pe) {
-        const double ykj = Y[(int64_t)k * ld + j];
-        const double w = ykj + scale * s_g[j - ps];         // v' * Y[:, j]   (v_k = 1)
-        const double t = tau * w;
-        Y[(int64_t)k * ld + j] = ykj - t;
-        tw[j - ps] = t;
-    }
-}
-
-// EXPERIMENTAL (option "qr.fast_house", default off, not yet run on hardware): the same step with
-// the reduction of the per-CTA partials spread over all 256 threads (16 slices per column, combined
-// in a fixed order) instead of 16 threads walking all `nparts` partials one after the other -- the
-// serial walk makes the single-CTA kernel 20 us per column (8.6 ms per randsvd at l = 210, and it
-// does not shrink with the row count, i.e. not with the number of GPUs).  Deterministic, but a
-// different summation order than qr_house_kernel (results agree to rounding, not bit for bit).
-__global__ void __launch_bounds__(QP_THREADS)
-qr_house2_kernel(double* __restrict__ Y, int64_t ld, int ps, int pe, int k, const double* __restrict__ partial,
                  int nparts, double* __restrict__ tw, double* __restrict__ taus, QrScal* __restrict__ scal) {
     __shared__ double s_red[QP_THREADS / QB][QB];
     __shared__ double s_g[QB];
@@ -206,6 +171,195 @@ qr_update_kernel(double* __restrict__ Y, int64_t ld, int64_t n, int ps, int pe, 
         }
     }
     panel_store_partials(psum, partial + (size_t)blockIdx.x * QB);
+}
+
+
+// ----------------------------------------------------------------------------- panel driver
+// One cooperative launch per panel [ps, pe).  CTA b owns rows [b*R, (b+1)*R) of Y; its rows >= ps
+// are active; the first `cap` owned rows live in shared memory (pitch QPK_PITCH: the 4 lanes x
+// 4 rows of a half-warp hit 16 distinct banks), the rest is worked on in place.  Exchange
+// buffers, double-buffered by column parity (rewritten only after two grid barriers):
+//   part [2][G][16]   per-CTA partial dot products of the current column with the panel columns
+//   krows[2][16]      the panel entries of row k, published by its owner
+constexpr int QPK_THREADS = 512;
+constexpr int QPK_WARPS = QPK_THREADS / 32;
+constexpr int QPK_PITCH = 20;
+constexpr int QPK_SLICES = QPK_THREADS / QB;      // 32 slices of the cross-CTA reduction
+
+struct QrPanelParams {
+    double* Y; int64_t ld; int64_t n; int ps, pe;
+    double* part; double* krows; double* taus;
+    int64_t R;
+    int cap;
+};
+
+__global__ void __launch_bounds__(QPK_THREADS, 1) qr_panel_kernel(const QrPanelParams p) {
+    cg::grid_group grid = cg::this_grid();
+    extern __shared__ double sm[];                 // [cap][QPK_PITCH]
+    __shared__ double s_red[QPK_SLICES][QB];
+    __shared__ double s_wpart[QPK_WARPS][QB];
+    __shared__ double s_g[QB], s_tw[QB];
+    __shared__ double s_scale;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, sub = lane & 3, rslot = tid >> 2;
+    const int G = (int)gridDim.x, b = (int)blockIdx.x;
+    const int pb = p.pe - p.ps;
+    const int64_t r0 = (int64_t)b * p.R;
+    const int64_t r1 = (r0 + p.R < p.n) ? r0 + p.R : p.n;
+    const int nown = r1 > r0 ? (int)(r1 - r0) : 0;
+    const int64_t ld = p.ld;
+    double* Ypan = p.Y + p.ps;
+    auto rowp = [&](int li) -> double* {
+        return li < p.cap ? sm + (size_t)li * QPK_PITCH : Ypan + (r0 + li) * ld;
+    };
+    auto first_local = [&](int64_t grow) -> int {       // first local row with global index >= grow
+        return grow > r0 ? (int)((grow - r0 < nown) ? grow - r0 : nown) : 0;
+    };
+    const int lfirst = first_local(p.ps);
+    const int nres = nown < p.cap ? nown : p.cap;
+    for (int li = lfirst + rslot; li < nres; li += QPK_THREADS / 4) {
+        const double* src = Ypan + (r0 + li) * ld;
+        double* dst = sm + (size_t)li * QPK_PITCH;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            const int j = sub + 4 * c;
+            if (j < pb) dst[j] = src[j];
+        }
+    }
+    __syncthreads();
+
+    // block reduction of the lanes' psum[c] (panel column sub + 4c) -> part[par][b][16];
+    // the owner of row `col` also publishes that row
+    auto publish = [&](int col, int par, double (&psum)[4]) {
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            double v = psum[c];
+            for (int o = 4; o < 32; o <<= 1) v += __shfl_xor_sync(0xffffffffu, v, o);   // over the 8 row slots
+            if (lane < 4) s_wpart[warp][sub + 4 * c] = v;
+        }
+        __syncthreads();                                   // also: all rows of this CTA are up to date
+        if (tid < QB) {
+            double s = 0.0;
+#pragma unroll
+            for (int w = 0; w < QPK_WARPS; ++w) s += s_wpart[w][tid];
+            p.part[((size_t)par * G + b) * QB + tid] = s;
+        } else if (tid >= 32 && tid < 32 + pb) {
+            if (col >= r0 && col < r1) p.krows[(size_t)par * QB + tid - 32] = rowp((int)(col - r0))[tid - 32];
+        }
+    };
+
+    // ---- dots of the first panel column with the panel columns, rows > ps
+    {
+        double psum[4] = {0.0, 0.0, 0.0, 0.0};
+        for (int li = first_local((int64_t)p.ps + 1) + rslot; li < nown; li += QPK_THREADS / 4) {
+            const double* row = rowp(li);
+            const double y0 = row[0];
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                const int j = sub + 4 * c;
+                if (j < pb) psum[c] = fma(y0, row[j], psum[c]);
+            }
+        }
+        publish(p.ps, 0, psum);
+    }
+    grid.sync();
+
+    for (int k = p.ps; k < p.pe; ++k) {
+        const int c = k - p.ps;
+        const int par = c & 1;
+        // ---- every CTA reduces the G partials in the same fixed order
+        {
+            const int j = tid % QB, slice = tid / QB;
+            double s = 0.0;
+            for (int q = slice; q < G; q += QPK_SLICES) s += __ldcg(p.part + ((size_t)par * G + q) * QB + j);
+            s_red[slice][j] = s;
+        }
+        __syncthreads();
+        if (tid < QB) {
+            double s = 0.0;
+#pragma unroll
+            for (int sl = 0; sl < QPK_SLICES; ++sl) s += s_red[sl][tid];
+            s_g[tid] = s;
+        }
+        __syncthreads();
+        // ---- Householder scalars (dlarfg), redundantly in every CTA; tw[j] = tau * (v' Y[:, j])
+        {
+            const double alpha = __ldcg(p.krows + (size_t)par * QB + c);
+            const double xnorm2 = s_g[c];
+            double tau = 0.0, scale = 0.0, beta = alpha;
+            if (xnorm2 > 0.0) {
+                const double nrm = sqrt(alpha * alpha + xnorm2);
+                beta = (alpha >= 0.0) ? -nrm : nrm;
+                tau = (beta - alpha) / beta;
+                scale = 1.0 / (alpha - beta);
+            }
+            if (tid == 0) {
+                s_scale = scale;
+                if (b == 0) p.taus[k] = tau;
+            }
+            const bool own_k = (k >= r0 && k < r1);
+            if (tid < pb) {
+                const int j = tid;
+                double t = 0.0;
+                if (j > c) {
+                    const double ykj = __ldcg(p.krows + (size_t)par * QB + j);
+                    const double w = ykj + scale * s_g[j];         // v' * Y[:, j]   (v_k = 1)
+                    t = tau * w;
+                    if (own_k) rowp((int)(k - r0))[j] = ykj - t;
+                } else if (j == c && own_k) {
+                    rowp((int)(k - r0))[c] = beta;
+                }
+                s_tw[j] = t;
+            }
+        }
+        __syncthreads();
+        // ---- rows i > k: v_i = scale * Y[i,k]; Y[i,j] -= v_i * tw[j]; dots of column k+1 (rows > k+1)
+        const double scale = s_scale;
+        double psum[4] = {0.0, 0.0, 0.0, 0.0};
+        const int lstart = first_local((int64_t)k + 1);
+        const int slot = c + 1;                              // panel slot of the next column
+        for (int base = lstart; base < nown; base += QPK_THREADS / 4) {      // warp-uniform trip count
+            const int li = base + rslot;
+            const bool valid = li < nown;
+            double nv[4] = {0.0, 0.0, 0.0, 0.0};
+            double* row = valid ? rowp(li) : sm;
+            const double a = valid ? row[c] : 0.0;
+            __syncwarp();                                   // all four lanes of a row have read a before it is replaced
+            if (valid) {
+                const double v = scale * a;
+#pragma unroll
+                for (int cc = 0; cc < 4; ++cc) {
+                    const int j = sub + 4 * cc;
+                    if (j >= c && j < pb) {
+                        nv[cc] = (j == c) ? v : row[j] - v * s_tw[j];
+                        row[j] = nv[cc];
+                    }
+                }
+            }
+            double mine = 0.0;
+#pragma unroll
+            for (int cc = 0; cc < 4; ++cc)
+                if (cc == (slot >> 2)) mine = nv[cc];
+            const double ynext = __shfl_sync(0xffffffffu, mine, (lane & ~3) | (slot & 3));
+            if (valid && r0 + li > (int64_t)k + 1) {
+#pragma unroll
+                for (int cc = 0; cc < 4; ++cc) psum[cc] = fma(ynext, nv[cc], psum[cc]);
+            }
+        }
+        if (k + 1 < p.pe) {
+            publish(k + 1, par ^ 1, psum);
+            grid.sync();
+        }
+    }
+    __syncthreads();
+    for (int li = lfirst + rslot; li < nres; li += QPK_THREADS / 4) {
+        double* dst = Ypan + (r0 + li) * ld;
+        const double* src = sm + (size_t)li * QPK_PITCH;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            const int j = sub + 4 * c;
+            if (j < pb) dst[j] = src[j];
+        }
+    }
 }
 
 // ----------------------------------------------------------------------------- Gram kernel
@@ -466,20 +620,57 @@ void qr_thinQ_inplace(gsi_ctx* ctx, gsi_buf* Y, double* Rdev) {
     const size_t need_doubles = (size_t)(gpart - ctx->scratch) + (size_t)ctx->num_sms * 16 * lpmax;
     GSI_REQUIRE(need_doubles <= ctx->scratch_doubles, GSI_ERR_UNSUPPORTED, "qr: scratch too small");
 
+    // panel driver set-up: cooperative grid of co-resident CTAs, at most one per SM
+    QrPanelParams pp;
+    int pgrid = 0;
+    size_t psmem = 0;
+    if (ctx->qr_panel) {
+        int64_t R = round_up((n + ctx->num_sms - 1) / ctx->num_sms, 8);
+        if (R < 256) R = 256;
+        pgrid = (int)((n + R - 1) / R);
+        int cap = (int)R;
+        if (cap > 1432) cap = 1432;                                     // x 160 B = 224 KB of the 227 KB a CTA may use
+        psmem = (size_t)cap * QPK_PITCH * sizeof(double);
+        GSI_CUDA(cudaFuncSetAttribute(qr_panel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psmem));
+        int occ = 0;
+        GSI_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, qr_panel_kernel, QPK_THREADS, psmem));
+        // exchange buffers live behind the Gram partials in the scratch area
+        double* xch = gpart + (size_t)ctx->num_sms * 16 * lpmax;
+        const size_t xneed = (size_t)2 * pgrid * QB + 2 * QB;
+        if (occ < 1 || pgrid > ctx->num_sms * occ || need_doubles + xneed > ctx->scratch_doubles) pgrid = 0;
+        if (pgrid > 0) {
+            pp.Y = Y->d; pp.ld = Y->ld; pp.n = n;
+            pp.part = xch; pp.krows = xch + (size_t)2 * pgrid * QB; pp.taus = taus;
+            pp.R = R; pp.cap = cap;
+        }
+    }
     // ---------------- factorisation, panel by panel
     for (int ps = 0, pi = 0; ps < l; ps += QB, ++pi) {
         const int pe = (ps + QB < l) ? ps + QB : l;
         double* T = Tall + (size_t)pi * QB * QB;
-        qr_panel_dots_kernel<<<grid, QP_THREADS, 0, st>>>(Y->d, Y->ld, n, ps, pe, partial);
-        for (int k = ps; k < pe; ++k) {
-            if (ctx->qr_fast_house)
-                qr_house2_kernel<<<1, QP_THREADS, 0, st>>>(Y->d, Y->ld, ps, pe, k, partial, grid, tw, taus, scal);
-            else
-                qr_house_kernel<<<1, QP_THREADS, 0, st>>>(Y->d, Y->ld, ps, pe, k, partial, grid, tw, taus, scal);
-            qr_update_kernel<<<grid, QP_THREADS, 0, st>>>(Y->d, Y->ld, n, ps, pe, k, tw, scal, partial);
+        bool done = false;
+        if (pgrid > 0) {
+            pp.ps = ps; pp.pe = pe;
+            void* args[] = {&pp};
+            const cudaError_t e = cudaLaunchCooperativeKernel((void*)qr_panel_kernel, dim3((unsigned)pgrid),
+                                                              dim3(QPK_THREADS), args, psmem, st);
+            if (e == cudaSuccess) {
+                count_launch(ctx);
+                done = true;
+            } else {
+                cudaGetLastError();            // the grid could not be made co-resident: per-column driver
+                pgrid = 0;
+            }
         }
-        GSI_CUDA(cudaGetLastError());
-        count_launch(ctx, 1 + 2 * (pe - ps));
+        if (!done) {
+            qr_panel_dots_kernel<<<grid, QP_THREADS, 0, st>>>(Y->d, Y->ld, n, ps, pe, partial);
+            for (int k = ps; k < pe; ++k) {
+                qr_house_kernel<<<1, QP_THREADS, 0, st>>>(Y->d, Y->ld, ps, pe, k, partial, grid, tw, taus, scal);
+                qr_update_kernel<<<grid, QP_THREADS, 0, st>>>(Y->d, Y->ld, n, ps, pe, k, tw, scal, partial);
+            }
+            GSI_CUDA(cudaGetLastError());
+            count_launch(ctx, 1 + 2 * (pe - ps));
+        }
         // T factor: G = V'V (rows >= pe through the Gram kernel, top block inside qr_tbuild)
         int nparts = 0, glp = 0;
         const int64_t rows_below = n - pe;

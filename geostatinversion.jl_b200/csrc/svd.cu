@@ -208,9 +208,11 @@ static cudaError_t launch_jacobi_fused(gsi_ctx* ctx, int nctas, int wpc, double*
                               ctx->jflags + JF_MAX_SWEEPS);
 }
 
+void svd_check(gsi_ctx* ctx);
+
 // Single-launch driver; returns false when the problem does not fit one cluster.
 static bool jacobi_sweeps_fused(gsi_ctx* ctx, double* M, int64_t ld, int rows_dot, int rows_all, int ncols, int np,
-                                double tol) {
+                                double tol, bool defer_check) {
     const int pairs = np / 2;
     if (pairs > JF_MAX_CTAS * 32 || ncols < 2) return false;
     int nctas = pairs < JF_MAX_CTAS ? pairs : JF_MAX_CTAS;
@@ -227,17 +229,27 @@ static bool jacobi_sweeps_fused(gsi_ctx* ctx, double* M, int64_t ld, int rows_do
         return false;
     }
     count_launch(ctx);
+    ctx->svd_pending = true;
+    if (!defer_check) svd_check(ctx);
+    return true;
+}
+
+// Convergence verdict of the last single-launch Jacobi run whose check was deferred (the randsvd
+// driver defers it to its one synchronisation point).  Synchronises the stream.
+void svd_check(gsi_ctx* ctx) {
+    if (!ctx->svd_pending) return;
+    ctx->svd_pending = false;
     int h = 0;
     GSI_CUDA(cudaMemcpyAsync(&h, ctx->jflags + JF_MAX_SWEEPS, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
     GSI_CUDA(cudaStreamSynchronize(ctx->stream));
     GSI_REQUIRE(h > 0, GSI_ERR_NO_CONVERGENCE, "Jacobi SVD did not converge in 60 sweeps");
-    return true;
 }
 
-void jacobi_sweeps(gsi_ctx* ctx, double* M, int64_t ld, int rows_dot, int rows_all, int ncols) {
+void jacobi_sweeps(gsi_ctx* ctx, double* M, int64_t ld, int rows_dot, int rows_all, int ncols, bool defer_check) {
     const int np = (ncols + 1) / 2 * 2;
     if (ctx->svd_fused &&
-        jacobi_sweeps_fused(ctx, M, ld, rows_dot, rows_all, ncols, np, sqrt((double)rows_dot) * 2.220446049250313e-16))
+        jacobi_sweeps_fused(ctx, M, ld, rows_dot, rows_all, ncols, np, sqrt((double)rows_dot) * 2.220446049250313e-16,
+                            defer_check))
         return;
     const int nrounds = np - 1;
     const int blocks = (np / 2 + JS_WARPS - 1) / JS_WARPS;
@@ -262,9 +274,9 @@ void jacobi_sweeps(gsi_ctx* ctx, double* M, int64_t ld, int rows_dot, int rows_a
 }
 
 // M: l x l column-major (ld = l), device.  U (l x l, ld = l) and sigma (l) device outputs.
-void svd_small(gsi_ctx* ctx, double* M, int l, double* U, double* sigma) {
+void svd_small(gsi_ctx* ctx, double* M, int l, double* U, double* sigma, bool defer_check) {
     GSI_REQUIRE(l >= 1 && l <= kMaxCols, GSI_ERR_UNSUPPORTED, "svd_small: l must be in 1..256");
-    jacobi_sweeps(ctx, M, l, l, l, l);
+    jacobi_sweeps(ctx, M, l, l, l, l, defer_check);
     jacobi_finalize_kernel<<<1, 1024, 0, ctx->stream>>>(M, l, U, sigma);
     GSI_CUDA(cudaGetLastError());
     count_launch(ctx);

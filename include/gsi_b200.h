@@ -111,16 +111,10 @@ int32_t gsi_ctx_phase_timing(gsi_ctx* ctx, double* ms_out8, int32_t reset);
  *   "kcov.epoch_shift"   epoch = 2^shift k-tiles of 32 points
  *   "svd.fused"          1 (default): the small Jacobi SVD (<= 512 columns) runs all sweeps in
  *                        one thread-block-cluster launch; 0: one launch per round (same rotations)
- *   "lu.fused"           EXPERIMENTAL, default 0, not yet verified on hardware: the column
- *                        steps of an LU panel run in one cooperative launch (rows all local)
- *   "lu.replicate"       EXPERIMENTAL, default 0: multi-GPU LU_REF normaliser gathers the iterate
- *                        and factors it redundantly on every rank (no per-column exchange)
- *   "qr.fast_house"      EXPERIMENTAL, default 0: Householder-scalar step of the QR panels with a
- *                        parallel (still deterministic) reduction of the per-CTA partial sums
- *   "kcov.pace"          EXPERIMENTAL, default 0: > 1 fetches each X tile of the structured-grid
- *                        product kernel as 4 bulk copies spread over the k-steps (burst probe)
- *   "kcov.prefetch"      EXPERIMENTAL, default 0: > 0 adds an L2 bulk prefetch of the X tile this
- *                        many k-tiles ahead of each CTA's sweep (structured-grid product kernel)
+ *   "lu.panel"           1 (default): one cooperative launch per 16-column LU panel, the panel rows
+ *                        resident in shared memory; 0: one launch pair per column (same pivots and
+ *                        arithmetic, bit-identical L)
+ *   "qr.panel"           1 (default): the same for the Householder QR panels; 0: launch pair per column
  * The environment variables GSI_SWEEP="groups,div,hint[,window[,epoch_shift]]" and
  * GSI_OPTIONS="name=value,name=value" set the same knobs at context creation.         */
 int32_t gsi_ctx_set_option(gsi_ctx* ctx, const char* name, int64_t value);

@@ -63,8 +63,6 @@ def main():
     ap.add_argument("--reps", type=int, default=2)
     ap.add_argument("--no-warm", action="store_true")
     ap.add_argument("--control", action="store_true", help="also time an L2-resident problem (X = 50 MB)")
-    ap.add_argument("--pace", type=int, default=0, help="kcov.pace (experimental paced X fetch)")
-    ap.add_argument("--prefetch", type=int, default=0, help="kcov.prefetch (experimental L2 prefetch, k-tiles ahead)")
     ap.add_argument("--generation", default="table", choices=["table", "arithmetic"],
                     help="kernel values from the lattice table (default) or from coordinates (no table look-ups "
                          "on the L2 return path: separates the two suspects of the L2-served-stream penalty)")
@@ -86,8 +84,6 @@ def main():
     X = gsi.DeviceMatrix.from_host(ctx, np.random.default_rng(0).standard_normal((n, l)))
     Y = gsi.DeviceMatrix(ctx, n, l)
     lib = ctx._lib
-    ctx.set_option("kcov.pace", args.pace)
-    ctx.set_option("kcov.prefetch", args.prefetch)
 
     def apply():
         gsi._lib.check(lib.gsi_op_apply(op._h, 0, X._h, Y._h))
