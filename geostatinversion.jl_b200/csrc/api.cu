@@ -174,6 +174,8 @@ GSI_API int32_t gsi_ctx_create(int32_t device, int32_t rank, int32_t world, cons
         GSI_CUDA(cudaMalloc(&ctx->dflags, 16 * sizeof(int)));
         GSI_CUDA(cudaMemset(ctx->dflags, 0, 16 * sizeof(int)));
         GSI_CUDA(cudaMalloc(&ctx->jflags, 64 * sizeof(int)));
+        GSI_CUDA(cudaMalloc(&ctx->pxch, kPxchDoubles * sizeof(double)));
+        GSI_CUDA(cudaMemset(ctx->pxch, 0, kPxchDoubles * sizeof(double)));
         if (const char* e = getenv("GSI_SVD_FUSED")) ctx->svd_fused = atoi(e) != 0;
         GSI_CUDA(cudaEventCreate(&ctx->ev0));
         GSI_CUDA(cudaEventCreate(&ctx->ev1));
@@ -196,6 +198,7 @@ static void ctx_really_destroy(gsi_ctx* ctx) {
     if (ctx->dflags) cudaFree(ctx->dflags);
     if (ctx->sweep_cnt) cudaFree(ctx->sweep_cnt);
     if (ctx->jflags) cudaFree(ctx->jflags);
+    if (ctx->pxch) cudaFree(ctx->pxch);
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
     for (cudaEvent_t e : ctx->ev_pool) cudaEventDestroy(e);
@@ -598,10 +601,11 @@ GSI_API int32_t gsi_qr_thinQ(gsi_ctx* ctx, gsi_buf* Y, double* R_host, int64_t l
             GSI_CUDA(cudaMalloc(&Rdev, (size_t)l * l * sizeof(double)));
         }
         std::unique_ptr<double, void (*)(double*)> guard(Rdev, [](double* p) { if (p) cudaFree(p); });
+        lu_reset_flag(ctx);
         qr_thinQ_inplace(ctx, Y, Rdev);
         if (R_host)
             GSI_CUDA(cudaMemcpy2DAsync(R_host, ldr * 8, Rdev, (size_t)l * 8, (size_t)l * 8, l, cudaMemcpyDeviceToHost, ctx->stream));
-        GSI_CUDA(cudaStreamSynchronize(ctx->stream));
+        lu_check_singular(ctx);              // synchronises; reports a panel-exchange time-out
     });
 }
 

@@ -39,6 +39,9 @@ inline int64_t round_up(int64_t x, int64_t m) { return (x + m - 1) / m * m; }
 
 constexpr int kRowPad = 64;        // tall buffers: allocated rows are a multiple of this
 constexpr int kMaxCols = 256;      // widest tall iterate a single GEMM pass handles
+constexpr int kPxchMaxCtas = 256;   // panel kernels: CTAs of one cooperative launch
+constexpr int kPxchRec = 40;        // doubles per published record
+constexpr size_t kPxchDoubles = (size_t)2 * kPxchMaxCtas * kPxchRec;
 
 // Width bookkeeping of the "tall" layout (row-major, row pitch ld doubles):
 //   lp = 8 * NB   (NB = number of 8-column DMMA blocks, from the instantiated list)
@@ -98,6 +101,8 @@ struct gsi_ctx {
     // launches per column (the first round's scheme, kept as the independent implementation to test against)
     int lu_panel = 1;
     int qr_panel = 1;
+    // exchange area of the panel kernels (used by nothing else): per-CTA records, double-buffered by column parity
+    double* pxch = nullptr;              // [kPxchDoubles]
 };
 
 struct gsi_buf {

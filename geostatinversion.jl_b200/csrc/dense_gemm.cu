@@ -29,8 +29,6 @@ struct DenseParams {
     int64_t kdim;         // reduction length (n for N, mloc for T)
     int64_t ld, ldw;
     double alpha;
-    int accumulate;       // 0: W = alpha*acc ; 1: W += alpha*acc on the first out_cols columns only
-    int64_t out_cols;
     int stages;
 };
 
@@ -105,7 +103,7 @@ dense_gemm_kernel(const __grid_constant__ CUtensorMap amap, const __grid_constan
             __syncwarp();
             const double* xs = smem + (size_t)s * stage_doubles;
             const double* as = xs + DG_BK * ld;
-#pragma unroll 2
+#pragma unroll
             for (int ks = 0; ks < DG_BK / 4; ++ks) {
                 const int j = ks * 4 + t;
                 const int r = rg * 16 + g;
@@ -135,18 +133,7 @@ dense_gemm_kernel(const __grid_constant__ CUtensorMap amap, const __grid_constan
                         double2 v;
                         v.x = p.alpha * acc[h][nb][0];
                         v.y = p.alpha * acc[h][nb][1];
-                        if (!p.accumulate) {
-                            *reinterpret_cast<double2*>(wrow + nb * 8) = v;
-                        } else {
-                            const int64_t col = (nb0 + nb) * 8 + 2 * t;     // masked read-modify-write
-                            if (col + 1 < p.out_cols) {
-                                double2 w = *reinterpret_cast<double2*>(wrow + nb * 8);
-                                w.x += v.x; w.y += v.y;
-                                *reinterpret_cast<double2*>(wrow + nb * 8) = w;
-                            } else if (col < p.out_cols) {
-                                wrow[nb * 8] += v.x;
-                            }
-                        }
+                        *reinterpret_cast<double2*>(wrow + nb * 8) = v;
                     }
                 }
             }
@@ -191,7 +178,7 @@ static void launch_dense(gsi_ctx* ctx, const gsi_buf* A, DenseParams p) {
     constexpr int a_inner = (TRANS ? DG_BK : DG_BM) + DG_PAD;
     constexpr int a_outer = TRANS ? DG_BM : DG_BK;
     constexpr size_t stage_bytes = (size_t)(DG_BK * ld + a_inner * a_outer) * sizeof(double);
-    int stages = (int)((200 * 1024) / stage_bytes);
+    int stages = (int)((232448 - 256) / stage_bytes);      // all 227 KB a CTA may use: 3 stages up to 224 columns
     if (stages > 4) stages = 4;
     if (stages < 2) stages = 2;
     p.stages = stages;
@@ -221,7 +208,6 @@ void dense_apply(gsi_ctx* ctx, const gsi_buf* A, int trans, const gsi_buf* X, gs
     GSI_REQUIRE(X->ld == 8 * nb + 4 && W->ld == X->ld, GSI_ERR_INVALID_ARGUMENT, "dense apply: bad pitch");
     DenseParams p;
     p.X = X->d; p.W = W->d; p.ld = X->ld; p.ldw = W->ld; p.alpha = alpha; p.stages = 0;
-    p.accumulate = 0; p.out_cols = X->cols;
     if (!trans) {
         GSI_REQUIRE(X->rows == A->cols, GSI_ERR_DIMENSION_MISMATCH, "dense apply: A*X inner dimension");
         GSI_REQUIRE(W->rows == A->rows, GSI_ERR_DIMENSION_MISMATCH, "dense apply: A*X output rows");
@@ -236,33 +222,6 @@ void dense_apply(gsi_ctx* ctx, const gsi_buf* A, int trans, const gsi_buf* X, gs
         GSI_NB_LIST(GSI_CASE)
 #undef GSI_CASE
         default: throw Error(GSI_ERR_UNSUPPORTED, "dense apply: unsupported column-block count");
-    }
-}
-
-// W[rows x ncols] (pointer + pitch, a window of a TALL buffer) += alpha * P * X, where P is a
-// rows x kdim window of a TALL buffer (pointer Pd, pitch ldp; seen by TMA as the column-major
-// matrix P' of size kdim x rows) and X is a small TALL buffer kdim x ncols.  Used for the
-// blocked LU / QR trailing updates (kdim = panel width <= 32).
-void tall_window_update(gsi_ctx* ctx, const double* Pd, int64_t ldp, int64_t rows, int64_t kdim, const gsi_buf* X,
-                        double* Wd, int64_t ldw, double alpha) {
-    if (rows <= 0 || X->cols <= 0 || kdim <= 0) return;
-    GSI_REQUIRE(X->layout == GSI_LAYOUT_TALL && X->rows == kdim, GSI_ERR_DIMENSION_MISMATCH, "window update: X rows");
-    GSI_REQUIRE(((uintptr_t)Pd % 16 == 0) && ((uintptr_t)Wd % 16 == 0) && (ldp % 2 == 0) && (ldw % 2 == 0),
-                GSI_ERR_INVALID_ARGUMENT, "window update: windows must be 16-byte aligned");
-    const int nb = nb_for_cols(X->cols);
-    GSI_REQUIRE(nb > 0 && X->ld == 8 * nb + 4, GSI_ERR_INVALID_ARGUMENT, "window update: bad X pitch");
-    gsi_buf view;
-    view.ctx = ctx; view.layout = GSI_LAYOUT_COLMAJOR; view.rows = kdim; view.cols = rows; view.ld = ldp;
-    view.d = const_cast<double*>(Pd); view.owns = false;
-    DenseParams p;
-    p.X = X->d; p.W = Wd; p.ld = X->ld; p.ldw = ldw; p.alpha = alpha; p.stages = 0;
-    p.accumulate = 1; p.out_cols = X->cols;
-    p.out_rows = rows; p.kdim = kdim;
-    switch (nb) {
-#define GSI_CASE(N) case N: launch_dense<N, 1>(ctx, &view, p); break;
-        GSI_NB_LIST(GSI_CASE)
-#undef GSI_CASE
-        default: throw Error(GSI_ERR_UNSUPPORTED, "window update: unsupported column-block count");
     }
 }
 

@@ -5,7 +5,8 @@
 // 8*n^2 bytes per step for a dense A -> HBM-bound), so it is built from small strided
 // vector kernels around op_apply with a single column; the stopping test needs one scalar
 // on the host per step.  Yfull / Qfull are kept column-major on the device because the
-// basis may outgrow the 256-column TALL limit while it is being built.
+// basis may outgrow the 256-column TALL limit while it is being built; `omegas` and `Q_out` may
+// be TALL (<= 256 columns) or COLMAJOR (any width, e.g. the default maxvec = min(m, n)).
 #include "common.cuh"
 #include "algos.h"
 
@@ -93,10 +94,18 @@ void rangefinder_adaptive(gsi_op* op, const gsi_buf* Omega0, const gsi_buf* omeg
                 "adaptive rangefinder needs a square operator (the reference allocates Yfull with n rows, RandMatFact.jl:18)");
     GSI_REQUIRE(Omega0->layout == GSI_LAYOUT_TALL && Omega0->rows == n && Omega0->cols == r, GSI_ERR_DIMENSION_MISMATCH,
                 "Omega0 must be TALL n x r");
-    GSI_REQUIRE(omegas->layout == GSI_LAYOUT_TALL && omegas->rows == n, GSI_ERR_DIMENSION_MISMATCH, "omegas must be TALL with n rows");
+    GSI_REQUIRE(omegas->rows == n, GSI_ERR_DIMENSION_MISMATCH, "omegas must have n rows");
     const int64_t maxvec = omegas->cols;
-    GSI_REQUIRE(Q_out->layout == GSI_LAYOUT_TALL && Q_out->rows == m && Q_out->cols == maxvec, GSI_ERR_DIMENSION_MISMATCH,
-                "Q_out must be TALL m x maxvec");
+    GSI_REQUIRE(Q_out->rows == m && Q_out->cols == maxvec, GSI_ERR_DIMENSION_MISMATCH, "Q_out must be m x maxvec");
+    GSI_REQUIRE((size_t)(maxvec + r + 2) <= ctx->scratch_doubles, GSI_ERR_UNSUPPORTED,
+                "adaptive rangefinder: maxvec + r exceeds the scratch area");
+    // element (i, c) of a TALL (row pitch ld) or COLMAJOR (column pitch ld) buffer: base + i * rs + c * cs
+    auto strides = [](const gsi_buf* b, int64_t& rs, int64_t& cs) {
+        if (b->layout == GSI_LAYOUT_TALL) { rs = b->ld; cs = 1; } else { rs = 1; cs = b->ld; }
+    };
+    int64_t om_rs, om_cs, qo_rs, qo_cs;
+    strides(omegas, om_rs, om_cs);
+    strides(Q_out, qo_rs, qo_cs);
     cudaStream_t st = ctx->stream;
     const int64_t ycols = r + maxvec;
     // column-major Yfull (n x (r+maxvec)) and Qfull (m x maxvec), zero initialised (:18, :23)
@@ -140,7 +149,7 @@ void rangefinder_adaptive(gsi_op* op, const gsi_buf* Omega0, const gsi_buf* omeg
         col_norms_kernel<<<1, 256, 0, st>>>(yj->d, yj->ld, m, nrm);
         scale_by_inv_norm_kernel<<<nblk(m), 256, 0, st>>>(yj->d, m, nrm, Qj);
         // Aomega = A * omega_j                                                              (:36-37)
-        strided_copy_kernel<<<nblk(n), 256, 0, st>>>(omegas->d + (j - 1), omegas->ld, colin->d, colin->ld, n);
+        strided_copy_kernel<<<nblk(n), 256, 0, st>>>(omegas->d + (j - 1) * om_cs, om_rs, colin->d, colin->ld, n);
         op_apply(op, 0, colin.get(), colout.get());
         // ynew = Aomega - Q (Q' Aomega) ; Yfull[:, r+j] = ynew                              (:38-40)
         colmat_t_vec_kernel<<<(unsigned)j, 256, 0, st>>>(Qf->d, Qf->ld, m, colout->d, colout->ld, cvec);
@@ -151,10 +160,115 @@ void rangefinder_adaptive(gsi_op* op, const gsi_buf* Omega0, const gsi_buf* omeg
         GSI_CUDA(cudaGetLastError());
         count_launch(ctx, 8);
     }
-    // Qfull[:, 1:j] -> TALL output
-    tall_zero(ctx, Q_out);
+    // Qfull[:, 1:j] -> output (columns beyond j are zero)
+    GSI_CUDA(cudaMemsetAsync(Q_out->d, 0, Q_out->bytes(), st));
     for (int64_t c = 0; c < j; ++c)
-        strided_copy_kernel<<<nblk(m), 256, 0, st>>>(Qf->d + c * Qf->ld, 1, Q_out->d + c, Q_out->ld, m);
+        strided_copy_kernel<<<nblk(m), 256, 0, st>>>(Qf->d + c * Qf->ld, 1, Q_out->d + c * qo_cs, qo_rs, m);
+    GSI_CUDA(cudaGetLastError());
+    count_launch(ctx, (int)j);
+    GSI_CUDA(cudaStreamSynchronize(st));
+    *j_out = j;
+}
+
+// ---- blocked adaptive range finder: opt-in, NOT the parity mode -------------
+// out[c] = ||Y[:, c]||_2 of a TALL buffer (one CTA per column)
+__global__ void tall_col_norms_kernel(const double* __restrict__ Y, int64_t ld, int64_t n, double* __restrict__ norms) {
+    const int c = blockIdx.x;
+    double s = 0.0;
+    for (int64_t i = threadIdx.x; i < n; i += blockDim.x) { const double v = Y[i * ld + c]; s += v * v; }
+    s = ex_block_sum(s);
+    if (threadIdx.x == 0) norms[c] = sqrt(s);
+}
+// Y -= T on the first `cols` columns of two TALL buffers of equal pitch
+__global__ void tall_sub_kernel(double* __restrict__ Y, const double* __restrict__ T, int64_t ld, int64_t n, int cols) {
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t i = idx / cols;
+    const int c = (int)(idx - i * cols);
+    if (i < n) Y[i * ld + c] -= T[i * ld + c];
+}
+
+// HMT algorithm 4.2 with the random vectors consumed a BLOCK at a time: Y = A * Omega_b is one
+// tensor-core GEMM pass over A instead of b GEMV passes (8 n^2 bytes per vector -> per block),
+// the projection against the basis found so far is block Gram-Schmidt with re-orthogonalisation
+// (two pairs of skinny GEMMs), the block is orthonormalised by the Householder QR (then projected
+// and orthonormalised once more, for blocks that overshoot the rank), and the
+// stopping test is the reference's estimator evaluated on the b fresh probes of a block:
+//     max_c ||(I - Q Q') A omega_c|| <= epsilon / (10 sqrt(2/pi)).
+// It draws the vectors in a different order of use than src/RandMatFact.jl:15-48 (all b columns
+// of a block join the basis together), so the basis -- and its size, rounded up to the block --
+// differ from the reference's: ||A - Q Q' A|| meets the same bound, the result is not bit-parity.
+void rangefinder_adaptive_blocked(gsi_op* op, const gsi_buf* omegas, double epsilon, int64_t block, gsi_buf* Q_out,
+                                  int64_t* j_out) {
+    gsi_ctx* ctx = op->ctx;
+    GSI_REQUIRE(ctx->world == 1, GSI_ERR_UNSUPPORTED, "adaptive rangefinder is single-GPU");
+    const int64_t m = op->m, n = op->n;
+    GSI_REQUIRE(block >= 1 && block <= kMaxCols && block <= m, GSI_ERR_INVALID_ARGUMENT,
+                "blocked adaptive rangefinder: 1 <= block <= min(256, m) required");
+    GSI_REQUIRE(omegas->rows == n, GSI_ERR_DIMENSION_MISMATCH, "omegas must have n rows");
+    const int64_t maxvec = omegas->cols;
+    GSI_REQUIRE(Q_out->rows == m && Q_out->cols == maxvec, GSI_ERR_DIMENSION_MISMATCH, "Q_out must be m x maxvec");
+    cudaStream_t st = ctx->stream;
+    int64_t om_rs, om_cs, qo_rs, qo_cs;
+    if (omegas->layout == GSI_LAYOUT_TALL) { om_rs = omegas->ld; om_cs = 1; } else { om_rs = 1; om_cs = omegas->ld; }
+    if (Q_out->layout == GSI_LAYOUT_TALL) { qo_rs = Q_out->ld; qo_cs = 1; } else { qo_rs = 1; qo_cs = Q_out->ld; }
+    BufPtr Qf = make_buf(ctx, GSI_LAYOUT_COLMAJOR, m, maxvec);
+    const double thresh = epsilon / sqrt(200.0 / M_PI);
+    double* norms = ctx->scratch;
+    std::vector<double> hn((size_t)block);
+    int64_t j = 0;
+    while (true) {
+        const int64_t b = (maxvec - j < block) ? maxvec - j : block;
+        if (b <= 0) {
+            *j_out = j;
+            throw Error(GSI_ERR_NO_CONVERGENCE, "adaptive rangefinder: maxvec basis vectors did not reach epsilon");
+        }
+        BufPtr Om = make_buf(ctx, GSI_LAYOUT_TALL, n, b);
+        for (int64_t c = 0; c < b; ++c)
+            strided_copy_kernel<<<nblk(n), 256, 0, st>>>(omegas->d + (j + c) * om_cs, om_rs, Om->d + c, Om->ld, n);
+        GSI_CUDA(cudaGetLastError());
+        count_launch(ctx, (int)b);
+        BufPtr Y = make_buf(ctx, GSI_LAYOUT_TALL, m, b);
+        op_apply(op, 0, Om.get(), Y.get());                                     // Y = A * Omega_b
+        // Y -= Q (Q' Y), `passes` times (block Gram-Schmidt against the basis found so far)
+        auto project = [&](int passes) {
+            if (j == 0) return;
+            gsi_buf qv = *Qf;
+            qv.owns = false; qv.cols = j;
+            BufPtr C = make_buf(ctx, GSI_LAYOUT_TALL, j, b);
+            BufPtr T = make_buf(ctx, GSI_LAYOUT_TALL, m, b);
+            for (int pass = 0; pass < passes; ++pass) {
+                dense_apply(ctx, &qv, 1, Y.get(), C.get(), 1.0);
+                dense_apply(ctx, &qv, 0, C.get(), T.get(), 1.0);
+                tall_sub_kernel<<<nblk(m * b), 256, 0, st>>>(Y->d, T->d, Y->ld, m, (int)b);
+                GSI_CUDA(cudaGetLastError());
+                count_launch(ctx, 3);
+            }
+        };
+        project(2);
+        tall_col_norms_kernel<<<(unsigned)b, 256, 0, st>>>(Y->d, Y->ld, m, norms);
+        GSI_CUDA(cudaMemcpyAsync(hn.data(), norms, b * sizeof(double), cudaMemcpyDeviceToHost, st));
+        GSI_CUDA(cudaStreamSynchronize(st));
+        count_launch(ctx);
+        double mx = 0.0;
+        for (int64_t c = 0; c < b; ++c) mx = hn[c] > mx ? hn[c] : mx;
+        if (!(mx > thresh)) break;
+        lu_reset_flag(ctx);
+        qr_thinQ_inplace(ctx, Y.get(), nullptr);                                // orthonormalise the block
+        // a block that overshoots the rank has columns of pure rounding noise whose directions are not
+        // orthogonal to the basis: project the orthonormalised block once more and re-orthonormalise
+        if (j > 0) {
+            project(1);
+            qr_thinQ_inplace(ctx, Y.get(), nullptr);
+        }
+        for (int64_t c = 0; c < b; ++c)
+            strided_copy_kernel<<<nblk(m), 256, 0, st>>>(Y->d + c, Y->ld, Qf->d + (j + c) * Qf->ld, 1, m);
+        GSI_CUDA(cudaGetLastError());
+        count_launch(ctx, (int)b);
+        j += b;
+    }
+    GSI_CUDA(cudaMemsetAsync(Q_out->d, 0, Q_out->bytes(), st));
+    for (int64_t c = 0; c < j; ++c)
+        strided_copy_kernel<<<nblk(m), 256, 0, st>>>(Qf->d + c * Qf->ld, 1, Q_out->d + c * qo_cs, qo_rs, m);
     GSI_CUDA(cudaGetLastError());
     count_launch(ctx, (int)j);
     GSI_CUDA(cudaStreamSynchronize(st));
@@ -278,6 +392,16 @@ GSI_API int32_t gsi_rangefinder_adaptive(gsi_op* op, const gsi_buf* Omega0, cons
         GSI_CUDA(cudaSetDevice(op->ctx->device));
         *j_out = 0;
         rangefinder_adaptive(op, Omega0, omegas, epsilon, r, Q_out, j_out);
+    });
+}
+
+GSI_API int32_t gsi_rangefinder_adaptive_blocked(gsi_op* op, const gsi_buf* omegas, double epsilon, int64_t block,
+                                                 gsi_buf* Q_out, int64_t* j_out) {
+    return guarded([&] {
+        GSI_REQUIRE(op && omegas && Q_out && j_out, GSI_ERR_INVALID_ARGUMENT, "null argument");
+        GSI_CUDA(cudaSetDevice(op->ctx->device));
+        *j_out = 0;
+        rangefinder_adaptive_blocked(op, omegas, epsilon, block, Q_out, j_out);
     });
 }
 

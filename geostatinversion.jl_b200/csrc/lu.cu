@@ -15,9 +15,10 @@
 // Panel factorisation, default driver (option "lu.panel" = 1): ONE cooperative launch per
 // panel, lu_panel_kernel.  Every CTA keeps its rows of the n x 16 panel in SHARED MEMORY for
 // the whole panel (rows beyond the shared-memory capacity stay in global memory / L2), so a
-// column step is: block arg-max -> publish (|v|, row, the candidate's 16 panel entries) ->
-// ONE grid barrier -> every CTA reduces the G candidates identically -> row interchange inside
-// the panel (each row by its owner) -> rank-1 update of its rows + the next column's arg-max.
+// column step is: block arg-max -> publish ONE record (|v|, row, the candidate's 16 panel entries,
+// row k's entries) -> ONE grid barrier -> every CTA reduces the G candidates identically -> row
+// interchange inside the panel (each row by its owner) -> rank-1 update of its rows + the next
+// column's arg-max.
 // The interchanges of the columns outside the panel are applied afterwards in one pass
 // (LAPACK's dlaswp order), by one CTA, while the others write their panel rows back.
 // l = 210: 14 launches with 16 grid barriers each instead of 420 launches + a host sync.
@@ -42,10 +43,8 @@
 // synchronisation point: lu_check_singular).
 #include "common.cuh"
 #include "algos.h"
-#include <cooperative_groups.h>
+#include "panel_xch.cuh"
 #include <cmath>
-
-namespace cg = cooperative_groups;
 
 namespace gsi {
 
@@ -189,17 +188,16 @@ lu_eliminate_kernel(double* __restrict__ Y, int64_t ld, int64_t nloc, int l, int
 }
 
 // ---------------------------------------------------------------------------- panel driver
-// One cooperative launch per panel [ps, pe).  CTA b owns rows [b*R, (b+1)*R) of Y (R a multiple
-// of 8); its rows >= ps are the "active" ones.  The first `cap` owned rows live in shared memory
-// (pitch LP_PITCH), the rest is worked on in place.  Exchange buffers are double-buffered by
-// column parity: a buffer of a given parity is rewritten only after two grid barriers, so a CTA
-// that already publishes for column k+1 cannot overwrite what a slower CTA still reads for k.
-//   cand [2][G]       best (|value|, row) of each CTA for the current column
-//   rows [2][G][16]   the panel entries of that candidate row
-//   krows[2][16]      the panel entries of row k, published by its owner
+// One cooperative launch per panel [ps, pe).  CTA b owns rows [b*R, (b+1)*R) of Y (R a multiple of 8); its rows
+// >= ps are the "active" ones.  The first `cap` owned rows live in shared memory (pitch LP_PITCH),
+// the rest is worked on in place.
+//
+// Exchange (panel_xch.cuh): per column step every CTA publishes ONE record, then the grid barrier:
+//     [ |candidate|, its row index, the candidate row's 16 panel entries, row k's 16 panel entries (owner only) ].
 struct LuPanelParams {
     double* Y; int64_t ld; int64_t n; int l; int ps, pe;
-    Cand* cand; double* rows; double* krows; int* flags;
+    double* recs;                   // [2][kPxchMaxCtas][kPxchRec]: val, idx, -, -, row[16], krow[16]
+    int* flags;
     int64_t R;
     int cap;
 };
@@ -216,7 +214,7 @@ __global__ void __launch_bounds__(LP_THREADS, 1) lu_panel_kernel(const LuPanelPa
     extern __shared__ double sm[];                 // [cap][LP_PITCH]
     __shared__ double s_bv[LP_WARPS], s_bi[LP_WARPS];
     __shared__ double s_prow[LU_PB], s_krow[LU_PB];
-    __shared__ double s_win[2];                    // pivot row index, winning CTA
+    __shared__ double s_win[2];                    // pivot row index
     __shared__ int s_piv[LU_PB];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, sub = lane & 3, rslot = tid >> 2;
     const int G = (int)gridDim.x, b = (int)blockIdx.x;
@@ -244,8 +242,10 @@ __global__ void __launch_bounds__(LP_THREADS, 1) lu_panel_kernel(const LuPanelPa
     }
     __syncthreads();
 
-    // block arg-max of (bv, bi) -> publish candidate + its row, and row `col` if I own it
-    auto publish = [&](int col, int par, double bv, double bi) {
+    // block arg-max of (bv, bi) -> my record of column step c: candidate + its row, and row `col` if I own it
+    auto publish = [&](int col, int c, double bv, double bi) {
+        const int par = c & 1;
+        double* rec = p.recs + ((size_t)par * kPxchMaxCtas + b) * kPxchRec;
         lp_warp_best(bv, bi);
         if (lane == 0) { s_bv[warp] = bv; s_bi[warp] = bi; }
         __syncthreads();                                   // also: all rows of this CTA are up to date
@@ -253,12 +253,12 @@ __global__ void __launch_bounds__(LP_THREADS, 1) lu_panel_kernel(const LuPanelPa
             bv = lane < LP_WARPS ? s_bv[lane] : -1.0;
             bi = lane < LP_WARPS ? s_bi[lane] : 0.0;
             lp_warp_best(bv, bi);
-            if (lane == 0) { p.cand[(size_t)par * G + b].val = bv; p.cand[(size_t)par * G + b].idx = bi; }
-            if (bv >= 0.0 && lane < pb)
-                p.rows[((size_t)par * G + b) * LU_PB + lane] = rowp((int)((int64_t)bi - r0))[lane];
+            if (lane == 0) { rec[0] = bv; rec[1] = bi; }
+            if (bv >= 0.0 && lane < pb) rec[4 + lane] = rowp((int)((int64_t)bi - r0))[lane];
         } else if (warp == 1) {
-            if (col >= r0 && col < r1 && lane < pb) p.krows[(size_t)par * LU_PB + lane] = rowp((int)(col - r0))[lane];
+            if (col >= r0 && col < r1 && lane < pb) rec[4 + LU_PB + lane] = rowp((int)(col - r0))[lane];
         }
+        grid.sync();                                       // every CTA's record of this column step is visible
     };
 
     // ---- candidates of the first column of the panel
@@ -273,17 +273,17 @@ __global__ void __launch_bounds__(LP_THREADS, 1) lu_panel_kernel(const LuPanelPa
         }
         publish(p.ps, 0, bv, bi);
     }
-    grid.sync();
 
     for (int k = p.ps; k < p.pe; ++k) {
         const int c = k - p.ps;
         const int par = c & 1;
         // ---- global pivot: every CTA reduces the G candidates the same way
         if (warp == 0) {
+            const double* recs = p.recs + (size_t)par * kPxchMaxCtas * kPxchRec;
             double bv = -1.0, bi = 0.0;
             int bw = 0;
             for (int q = lane; q < G; q += 32) {
-                const double v = __ldcg(&p.cand[(size_t)par * G + q].val), i = __ldcg(&p.cand[(size_t)par * G + q].idx);
+                const double v = __ldcg(recs + (size_t)q * kPxchRec), i = __ldcg(recs + (size_t)q * kPxchRec + 1);
                 if (v >= 0.0 && cand_better(v, i, bv, bi)) { bv = v; bi = i; bw = q; }
             }
             for (int o = 1; o < 32; o <<= 1) {
@@ -292,9 +292,10 @@ __global__ void __launch_bounds__(LP_THREADS, 1) lu_panel_kernel(const LuPanelPa
                 if (cand_better(ov, oi, bv, bi)) { bv = ov; bi = oi; bw = ow; }
             }
             if (bv < 0.0) { bi = (double)k; }            // no row left (cannot happen for n >= l): no interchange
+            const int owner_k = (int)(k / p.R);
             if (lane < pb) {
-                s_krow[lane] = __ldcg(p.krows + (size_t)par * LU_PB + lane);
-                s_prow[lane] = bv >= 0.0 ? __ldcg(p.rows + ((size_t)par * G + bw) * LU_PB + lane) : s_krow[lane];
+                s_krow[lane] = __ldcg(recs + (size_t)owner_k * kPxchRec + 4 + LU_PB + lane);
+                s_prow[lane] = bv >= 0.0 ? __ldcg(recs + (size_t)bw * kPxchRec + 4 + lane) : s_krow[lane];
             }
             if (lane == 0) { s_win[0] = bi; s_piv[c] = (int)bi; }
         }
@@ -346,10 +347,7 @@ __global__ void __launch_bounds__(LP_THREADS, 1) lu_panel_kernel(const LuPanelPa
                 }
             }
         }
-        if (k + 1 < p.pe) {
-            publish(k + 1, par ^ 1, bv, bi);
-            grid.sync();
-        }
+        if (k + 1 < p.pe) publish(k + 1, c + 1, bv, bi);
     }
     __syncthreads();
     // ---- write my resident rows back
@@ -410,7 +408,7 @@ __global__ void lu_finalize_kernel(double* __restrict__ Y, int64_t ld, int64_t n
 }
 
 void lu_reset_flag(gsi_ctx* ctx) {
-    GSI_CUDA(cudaMemsetAsync(ctx->dflags, 0, sizeof(int), ctx->stream));
+    GSI_CUDA(cudaMemsetAsync(ctx->dflags, 0, sizeof(int), ctx->stream));          // [0] first zero pivot
 }
 
 // Synchronises the stream and throws SingularException if an LU since the last reset met an
@@ -449,19 +447,18 @@ void lu_L_inplace(gsi_ctx* ctx, gsi_buf* Y) {
         if (R < rmin) R = rmin;
         pgrid = (int)((n + R - 1) / R);
         int cap = (int)R;
-        const int cap_max = 1432;                                       // x 160 B = 224 KB of the 227 KB a CTA may use
+        cudaFuncAttributes fa;
+        GSI_CUDA(cudaFuncGetAttributes(&fa, lu_panel_kernel));
+        const int cap_max = (int)((232448 - fa.sharedSizeBytes) / (LP_PITCH * sizeof(double)));   // 227 KB per CTA, minus the static part
         if (cap > cap_max) cap = cap_max;
         psmem = (size_t)cap * LP_PITCH * sizeof(double);
         GSI_CUDA(cudaFuncSetAttribute(lu_panel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psmem));
         int occ = 0;
         GSI_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, lu_panel_kernel, LP_THREADS, psmem));
-        const size_t pneed = (size_t)2 * pgrid * 2 + (size_t)2 * pgrid * LU_PB + 2 * LU_PB + 16;
-        if (occ < 1 || pgrid > ctx->num_sms * occ || pneed > ctx->scratch_doubles) pgrid = 0;   // per-column driver instead
+        if (occ < 1 || pgrid > ctx->num_sms * occ || pgrid > kPxchMaxCtas) pgrid = 0;   // per-column driver instead
         if (pgrid > 0) {
             pp.Y = Y->d; pp.ld = Y->ld; pp.n = n; pp.l = l;
-            pp.cand = reinterpret_cast<Cand*>(ctx->scratch);
-            pp.rows = ctx->scratch + (size_t)2 * pgrid * 2;
-            pp.krows = pp.rows + (size_t)2 * pgrid * LU_PB;
+            pp.recs = ctx->pxch;
             pp.flags = ctx->dflags;
             pp.R = R; pp.cap = cap;
         }

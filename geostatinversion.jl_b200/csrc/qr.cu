@@ -26,17 +26,15 @@
 #include "algos.h"
 #include "ptx.cuh"
 #include "nb_list.h"
-#include <cooperative_groups.h>
-
-namespace cg = cooperative_groups;
+#include "panel_xch.cuh"
 
 namespace gsi {
 
 constexpr int QB = 16;               // panel width
 constexpr int QP_THREADS = 256;      // panel column-step kernels
 constexpr int QP_WARPS = QP_THREADS / 32;
-constexpr int GR_THREADS = 256;      // Gram kernel: 8 warps, each a private row chunk
-constexpr int GR_WARPS = GR_THREADS / 32;
+constexpr int GR_THREADS = 512;      // Gram kernel: 16 warps = 4 row chunks x 4 column groups
+constexpr int GR_RC = GR_THREADS / 32 / 4;
 
 struct QrScal { double tau, scale, beta, pad; };
 
@@ -175,12 +173,11 @@ qr_update_kernel(double* __restrict__ Y, int64_t ld, int64_t n, int ps, int pe, 
 
 
 // ----------------------------------------------------------------------------- panel driver
-// One cooperative launch per panel [ps, pe).  CTA b owns rows [b*R, (b+1)*R) of Y; its rows >= ps
-// are active; the first `cap` owned rows live in shared memory (pitch QPK_PITCH: the 4 lanes x
-// 4 rows of a half-warp hit 16 distinct banks), the rest is worked on in place.  Exchange
-// buffers, double-buffered by column parity (rewritten only after two grid barriers):
-//   part [2][G][16]   per-CTA partial dot products of the current column with the panel columns
-//   krows[2][16]      the panel entries of row k, published by its owner
+// One cooperative launch per panel [ps, pe).  CTA b owns
+// rows [b*R, (b+1)*R) of Y; its rows >= ps are active; the first `cap` owned rows live in shared
+// memory (pitch QPK_PITCH: the 4 lanes x 4 rows of a half-warp hit 16 distinct banks), the rest
+// is worked on in place.  Per column step every CTA publishes ONE record (panel_xch.cuh), then the grid barrier:
+//     [ its 16 partial dot products of column k with the panel columns, row k's 16 panel entries (owner only) ].
 constexpr int QPK_THREADS = 512;
 constexpr int QPK_WARPS = QPK_THREADS / 32;
 constexpr int QPK_PITCH = 20;
@@ -188,7 +185,8 @@ constexpr int QPK_SLICES = QPK_THREADS / QB;      // 32 slices of the cross-CTA 
 
 struct QrPanelParams {
     double* Y; int64_t ld; int64_t n; int ps, pe;
-    double* part; double* krows; double* taus;
+    double* recs;                   // [2][kPxchMaxCtas][kPxchRec]: part[16], krow[16]
+    double* taus;
     int64_t R;
     int cap;
 };
@@ -227,24 +225,27 @@ __global__ void __launch_bounds__(QPK_THREADS, 1) qr_panel_kernel(const QrPanelP
     }
     __syncthreads();
 
-    // block reduction of the lanes' psum[c] (panel column sub + 4c) -> part[par][b][16];
+    // block reduction of the lanes' psum[cc] (panel column sub + 4cc) -> my record of column step c;
     // the owner of row `col` also publishes that row
-    auto publish = [&](int col, int par, double (&psum)[4]) {
+    auto publish = [&](int col, int c, double (&psum)[4]) {
+        const int par = c & 1;
+        double* rec = p.recs + ((size_t)par * kPxchMaxCtas + b) * kPxchRec;
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {
-            double v = psum[c];
+        for (int cc = 0; cc < 4; ++cc) {
+            double v = psum[cc];
             for (int o = 4; o < 32; o <<= 1) v += __shfl_xor_sync(0xffffffffu, v, o);   // over the 8 row slots
-            if (lane < 4) s_wpart[warp][sub + 4 * c] = v;
+            if (lane < 4) s_wpart[warp][sub + 4 * cc] = v;
         }
         __syncthreads();                                   // also: all rows of this CTA are up to date
         if (tid < QB) {
             double s = 0.0;
 #pragma unroll
             for (int w = 0; w < QPK_WARPS; ++w) s += s_wpart[w][tid];
-            p.part[((size_t)par * G + b) * QB + tid] = s;
+            rec[tid] = s;
         } else if (tid >= 32 && tid < 32 + pb) {
-            if (col >= r0 && col < r1) p.krows[(size_t)par * QB + tid - 32] = rowp((int)(col - r0))[tid - 32];
+            if (col >= r0 && col < r1) rec[QB + tid - 32] = rowp((int)(col - r0))[tid - 32];
         }
+        grid.sync();                                       // every CTA's record of this column step is visible
     };
 
     // ---- dots of the first panel column with the panel columns, rows > ps
@@ -261,16 +262,19 @@ __global__ void __launch_bounds__(QPK_THREADS, 1) qr_panel_kernel(const QrPanelP
         }
         publish(p.ps, 0, psum);
     }
-    grid.sync();
 
     for (int k = p.ps; k < p.pe; ++k) {
         const int c = k - p.ps;
         const int par = c & 1;
+        const double* recs = p.recs + (size_t)par * kPxchMaxCtas * kPxchRec;
+        const double* krow = recs + (size_t)(k / p.R) * kPxchRec + QB;     // published by the owner of row k
+        const double alpha = __ldcg(krow + c);                             // (issued together with the partials)
+        const double ykj_mine = (tid < pb) ? __ldcg(krow + tid) : 0.0;
         // ---- every CTA reduces the G partials in the same fixed order
         {
             const int j = tid % QB, slice = tid / QB;
             double s = 0.0;
-            for (int q = slice; q < G; q += QPK_SLICES) s += __ldcg(p.part + ((size_t)par * G + q) * QB + j);
+            for (int q = slice; q < G; q += QPK_SLICES) s += __ldcg(recs + (size_t)q * kPxchRec + j);
             s_red[slice][j] = s;
         }
         __syncthreads();
@@ -283,7 +287,6 @@ __global__ void __launch_bounds__(QPK_THREADS, 1) qr_panel_kernel(const QrPanelP
         __syncthreads();
         // ---- Householder scalars (dlarfg), redundantly in every CTA; tw[j] = tau * (v' Y[:, j])
         {
-            const double alpha = __ldcg(p.krows + (size_t)par * QB + c);
             const double xnorm2 = s_g[c];
             double tau = 0.0, scale = 0.0, beta = alpha;
             if (xnorm2 > 0.0) {
@@ -301,7 +304,7 @@ __global__ void __launch_bounds__(QPK_THREADS, 1) qr_panel_kernel(const QrPanelP
                 const int j = tid;
                 double t = 0.0;
                 if (j > c) {
-                    const double ykj = __ldcg(p.krows + (size_t)par * QB + j);
+                    const double ykj = ykj_mine;
                     const double w = ykj + scale * s_g[j];         // v' * Y[:, j]   (v_k = 1)
                     t = tau * w;
                     if (own_k) rowp((int)(k - r0))[j] = ykj - t;
@@ -345,10 +348,7 @@ __global__ void __launch_bounds__(QPK_THREADS, 1) qr_panel_kernel(const QrPanelP
                 for (int cc = 0; cc < 4; ++cc) psum[cc] = fma(ynext, nv[cc], psum[cc]);
             }
         }
-        if (k + 1 < p.pe) {
-            publish(k + 1, par ^ 1, psum);
-            grid.sync();
-        }
+        if (k + 1 < p.pe) publish(k + 1, c + 1, psum);
     }
     __syncthreads();
     for (int li = lfirst + rslot; li < nres; li += QPK_THREADS / 4) {
@@ -365,6 +365,9 @@ __global__ void __launch_bounds__(QPK_THREADS, 1) qr_panel_kernel(const QrPanelP
 // ----------------------------------------------------------------------------- Gram kernel
 // partial[cta][a][j] = sum over this CTA's rows of P1[i, a] * P2[i, j],  a < 16, j < 8*NB.
 // P1 / P2 are windows of TALL buffers (pointer + pitch); columns >= c1 / >= c2 read as zero.
+// A streaming kernel (2 flops per byte of P2 at 16 panel columns): 16 warps = 4 row chunks x 4
+// column groups per CTA, and every warp issues the loads of 8-16 rows (2-4 k-steps) before the
+// first MMA of the group, so that 16-30 independent loads per lane are in flight.
 template <int NB>
 __global__ void __launch_bounds__(GR_THREADS)
 gram_kernel(const double* __restrict__ P1, int64_t ld1, int c1, const double* __restrict__ P2, int64_t ld2, int c2,
@@ -374,13 +377,13 @@ gram_kernel(const double* __restrict__ P1, int64_t ld1, int c1, const double* __
     constexpr int lp = 8 * NB;
     constexpr int NBW = (NB + 3) / 4;                   // n-blocks per warp (4 column groups)
     for (int i = threadIdx.x; i < 16 * lp; i += GR_THREADS) s_tile[i] = 0.0;
-    // 8 warps = 2 row chunks x 4 column groups; a row chunk is contiguous, multiple of 4 rows
+    // a row chunk is contiguous, a multiple of 16 rows
     const int cg = warp & 3, rc = warp >> 2;
     const int nb0 = cg * NBW;
-    const int64_t nchunks = (int64_t)gridDim.x * 2;
+    const int64_t nchunks = (int64_t)gridDim.x * GR_RC;
     int64_t chunk = (rows + nchunks - 1) / nchunks;
-    chunk = (chunk + 3) / 4 * 4;
-    const int64_t r0 = ((int64_t)blockIdx.x * 2 + rc) * chunk;
+    chunk = (chunk + 15) / 16 * 16;
+    const int64_t r0 = ((int64_t)blockIdx.x * GR_RC + rc) * chunk;
     int64_t r1 = r0 + chunk;
     if (r1 > rows) r1 = rows;
     double acc[2][NBW][2];
@@ -389,24 +392,34 @@ gram_kernel(const double* __restrict__ P1, int64_t ld1, int c1, const double* __
 #pragma unroll
         for (int nb = 0; nb < NBW; ++nb) { acc[h][nb][0] = 0.0; acc[h][nb][1] = 0.0; }
     const bool a0ok = g < c1, a1ok = 8 + g < c1;
-    for (int64_t i0 = r0; i0 < r1; i0 += 4) {
-        const int64_t i = i0 + t;
-        const bool rok = i < r1;
-        const double a0 = (rok && a0ok) ? P1[i * ld1 + g] : 0.0;
-        const double a1 = (rok && a1ok) ? P1[i * ld1 + 8 + g] : 0.0;
-        const double* p2 = P2 + i * ld2 + nb0 * 8 + g;
+    bool bok[NBW];
 #pragma unroll
-        for (int nb = 0; nb < NBW; ++nb) {
-            if (nb0 + nb < NB) {
-                const double b = (rok && (nb0 + nb) * 8 + g < c2) ? p2[nb * 8] : 0.0;
-                dmma884(acc[0][nb][0], acc[0][nb][1], a0, b);
-                dmma884(acc[1][nb][0], acc[1][nb][1], a1, b);
+    for (int nb = 0; nb < NBW; ++nb) bok[nb] = (nb0 + nb < NB) && ((nb0 + nb) * 8 + g < c2);
+    constexpr int KS = NBW >= 8 ? 1 : (NBW >= 5 ? 2 : 4);               // k-steps (of 4 rows) loaded ahead of their MMAs: register budget
+    for (int64_t i0 = r0; i0 < r1; i0 += 4 * KS) {
+        double a0[KS], a1[KS], bb[KS][NBW];
+#pragma unroll
+        for (int ks = 0; ks < KS; ++ks) {
+            const int64_t i = i0 + 4 * ks + t;
+            const bool rok = i < r1;
+            a0[ks] = (rok && a0ok) ? P1[i * ld1 + g] : 0.0;
+            a1[ks] = (rok && a1ok) ? P1[i * ld1 + 8 + g] : 0.0;
+            const double* p2 = P2 + i * ld2 + nb0 * 8 + g;
+#pragma unroll
+            for (int nb = 0; nb < NBW; ++nb) bb[ks][nb] = (rok && bok[nb]) ? p2[nb * 8] : 0.0;
+        }
+#pragma unroll
+        for (int ks = 0; ks < KS; ++ks) {
+#pragma unroll
+            for (int nb = 0; nb < NBW; ++nb) {          // n-blocks beyond NB multiply zeros (never stored)
+                dmma884(acc[0][nb][0], acc[0][nb][1], a0[ks], bb[ks][nb]);
+                dmma884(acc[1][nb][0], acc[1][nb][1], a1[ks], bb[ks][nb]);
             }
         }
     }
     __syncthreads();
-    // deterministic accumulation: column groups are disjoint, the two row chunks add in order
-    for (int w = 0; w < 2; ++w) {
+    // deterministic accumulation: column groups are disjoint, the row chunks add in order
+    for (int w = 0; w < GR_RC; ++w) {
         if (rc == w) {
 #pragma unroll
             for (int h = 0; h < 2; ++h)
@@ -440,7 +453,7 @@ static void gram(gsi_ctx* ctx, const double* P1, int64_t ld1, int c1, const doub
     GSI_REQUIRE(nb > 0, GSI_ERR_UNSUPPORTED, "gram: too many columns");
     lp = 8 * nb;
     int64_t grid = ctx->num_sms;
-    const int64_t need = (rows + 2 * 256 - 1) / (2 * 256);
+    const int64_t need = (rows + GR_RC * 128 - 1) / (GR_RC * 128);
     if (grid > need) grid = need > 0 ? need : 1;
     nparts = (int)grid;
     switch (nb) {
@@ -489,53 +502,49 @@ __global__ void qr_tbuild_kernel(const double* __restrict__ Y, int64_t ld, int p
     T[c * QB + a] = Ts[a][c];
 }
 
-// One thread per trailing column j (window column jj): W = V'Y2 (Gram partials over rows >= pe
-// + top block), W2 = op(T) W  (transT = 1: T'W, factorisation; 0: T W, forming Q),
-// top rows Y2[ps+r, j] -= sum_c V_top[r][c] W2[c], and W2 -> TALL buffer for the GEMM update.
-__global__ void qr_wt_kernel(double* __restrict__ Y, int64_t ld, int ps, int pe, int j0, int ncols,
-                             const double* __restrict__ wpart, int nparts, int wlp, const double* __restrict__ T,
-                             int transT, double* __restrict__ W2, int64_t ldw2) {
-    __shared__ double Ts[QB][QB], Vt[QB][QB];
+// A CTA of 256 threads handles 16 trailing columns (window columns jj0 .. jj0+15): W = V'Y2 (Gram
+// partials over rows >= pe, summed by all threads: thread (c, jj) walks the nparts partials of its
+// own entry, + the top block), W2 = op(T) W (transT = 1: T'W, factorisation; 0: T W, forming Q),
+// top rows Y2[ps+r, j] -= sum_c V_top[r][c] W2[c], and W2 -> TALL buffer for the rank-16 update.
+__global__ void __launch_bounds__(QB * QB)
+qr_wt_kernel(double* __restrict__ Y, int64_t ld, int ps, int pe, int j0, int ncols,
+             const double* __restrict__ wpart, int nparts, int wlp, const double* __restrict__ T,
+             int transT, double* __restrict__ W2, int64_t ldw2) {
+    __shared__ double Ts[QB][QB], Vt[QB][QB], y2[QB][QB + 1], w[QB][QB + 1], w2[QB][QB + 1];
     const int pb = pe - ps;
-    for (int i = threadIdx.x; i < QB * QB; i += blockDim.x) {
-        const int r = i / QB, c = i % QB;
-        Ts[r][c] = (r < pb && c < pb) ? T[c * QB + r] : 0.0;
-        Vt[r][c] = (r < pb && c < pb) ? vtop(Y, ld, ps, r, c) : 0.0;
+    const int a = threadIdx.x / QB, jl = threadIdx.x % QB;          // a: panel index (row r / column c), jl: local column
+    const int jj = blockIdx.x * QB + jl;
+    const bool colok = jj < ncols;
+    const int j = j0 + jj;
+    Ts[a][jl] = (a < pb && jl < pb) ? T[jl * QB + a] : 0.0;         // Ts[r][c] = T(r, c)
+    Vt[a][jl] = (a < pb && jl < pb) ? vtop(Y, ld, ps, a, jl) : 0.0;
+    y2[a][jl] = (a < pb && colok) ? Y[(int64_t)(ps + a) * ld + j] : 0.0;
+    __syncthreads();
+    {
+        double s = 0.0;
+        if (a < pb && colok) {
+            const double* wp = wpart + (size_t)a * wlp + jj;
+#pragma unroll 8
+            for (int b = 0; b < nparts; ++b) s += wp[(size_t)b * 16 * wlp];
+#pragma unroll
+            for (int r = 0; r < QB; ++r) s += Vt[r][a] * y2[r][jl];
+        }
+        w[a][jl] = s;
     }
     __syncthreads();
-    const int jj = blockIdx.x * blockDim.x + threadIdx.x;
-    if (jj >= ncols) return;
-    const int j = j0 + jj;
-    double w[QB], y2[QB];
-#pragma unroll
-    for (int r = 0; r < QB; ++r) y2[r] = (r < pb) ? Y[(int64_t)(ps + r) * ld + j] : 0.0;
-#pragma unroll
-    for (int c = 0; c < QB; ++c) {
-        double s = 0.0;
-        if (c < pb) {
-            for (int b = 0; b < nparts; ++b) s += wpart[(size_t)b * 16 * wlp + c * wlp + jj];
-#pragma unroll
-            for (int r = 0; r < QB; ++r) s += Vt[r][c] * y2[r];
-        }
-        w[c] = s;
-    }
-    double w2[QB];
-#pragma unroll
-    for (int c = 0; c < QB; ++c) {
+    {
         double s = 0.0;
 #pragma unroll
-        for (int m = 0; m < QB; ++m) s += (transT ? Ts[m][c] : Ts[c][m]) * w[m];
-        w2[c] = s;
+        for (int m = 0; m < QB; ++m) s += (transT ? Ts[m][a] : Ts[a][m]) * w[m][jl];
+        w2[a][jl] = s;
     }
+    __syncthreads();
+    if (a < pb && colok) {
+        double s = y2[a][jl];
 #pragma unroll
-    for (int r = 0; r < QB; ++r) {
-        if (r < pb) {
-            double s = y2[r];
-#pragma unroll
-            for (int c = 0; c < QB; ++c) s -= Vt[r][c] * w2[c];
-            Y[(int64_t)(ps + r) * ld + j] = s;
-            W2[(int64_t)r * ldw2 + jj] = w2[r];
-        }
+        for (int c = 0; c < QB; ++c) s -= Vt[a][c] * w2[c][jl];
+        Y[(int64_t)(ps + a) * ld + j] = s;
+        W2[(int64_t)a * ldw2 + jj] = w2[a][jl];
     }
 }
 
@@ -629,18 +638,19 @@ void qr_thinQ_inplace(gsi_ctx* ctx, gsi_buf* Y, double* Rdev) {
         if (R < 256) R = 256;
         pgrid = (int)((n + R - 1) / R);
         int cap = (int)R;
-        if (cap > 1432) cap = 1432;                                     // x 160 B = 224 KB of the 227 KB a CTA may use
+        cudaFuncAttributes fa;
+        GSI_CUDA(cudaFuncGetAttributes(&fa, qr_panel_kernel));
+        const int cap_max = (int)((232448 - fa.sharedSizeBytes) / (QPK_PITCH * sizeof(double)));   // 227 KB per CTA, minus the static part
+        if (cap > cap_max) cap = cap_max;
         psmem = (size_t)cap * QPK_PITCH * sizeof(double);
         GSI_CUDA(cudaFuncSetAttribute(qr_panel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psmem));
         int occ = 0;
         GSI_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, qr_panel_kernel, QPK_THREADS, psmem));
-        // exchange buffers live behind the Gram partials in the scratch area
-        double* xch = gpart + (size_t)ctx->num_sms * 16 * lpmax;
-        const size_t xneed = (size_t)2 * pgrid * QB + 2 * QB;
-        if (occ < 1 || pgrid > ctx->num_sms * occ || need_doubles + xneed > ctx->scratch_doubles) pgrid = 0;
+        if (occ < 1 || pgrid > ctx->num_sms * occ || pgrid > kPxchMaxCtas) pgrid = 0;
         if (pgrid > 0) {
             pp.Y = Y->d; pp.ld = Y->ld; pp.n = n;
-            pp.part = xch; pp.krows = xch + (size_t)2 * pgrid * QB; pp.taus = taus;
+            pp.recs = ctx->pxch;
+            pp.taus = taus;
             pp.R = R; pp.cap = cap;
         }
     }
@@ -686,7 +696,7 @@ void qr_thinQ_inplace(gsi_ctx* ctx, gsi_buf* Y, double* Rdev) {
             gram(ctx, Y->d + (int64_t)pe * Y->ld + ps, Y->ld, pe - ps, Y->d + (int64_t)pe * Y->ld + pe, Y->ld, ncols,
                  rows_below, gpart, wparts, wlp);
             BufPtr W2 = make_buf(ctx, GSI_LAYOUT_TALL, pe - ps, ncols);
-            qr_wt_kernel<<<(ncols + 63) / 64, 64, 0, st>>>(Y->d, Y->ld, ps, pe, pe, ncols, gpart, wparts, wlp, T, 1,
+            qr_wt_kernel<<<(ncols + QB - 1) / QB, QB * QB, 0, st>>>(Y->d, Y->ld, ps, pe, pe, ncols, gpart, wparts, wlp, T, 1,
                                                            W2->d, W2->ld);
             GSI_CUDA(cudaGetLastError());
             count_launch(ctx);
@@ -714,7 +724,7 @@ void qr_thinQ_inplace(gsi_ctx* ctx, gsi_buf* Y, double* Rdev) {
             gram(ctx, Y->d + (int64_t)pe * Y->ld + ps, Y->ld, pe - ps, Y->d + (int64_t)pe * Y->ld + pe, Y->ld, ncols,
                  rows_below, gpart, wparts, wlp);
             BufPtr W2 = make_buf(ctx, GSI_LAYOUT_TALL, pe - ps, ncols);
-            qr_wt_kernel<<<(ncols + 63) / 64, 64, 0, st>>>(Y->d, Y->ld, ps, pe, pe, ncols, gpart, wparts, wlp, T, 0,
+            qr_wt_kernel<<<(ncols + QB - 1) / QB, QB * QB, 0, st>>>(Y->d, Y->ld, ps, pe, pe, ncols, gpart, wparts, wlp, T, 0,
                                                            W2->d, W2->ld);
             GSI_CUDA(cudaGetLastError());
             count_launch(ctx);

@@ -8,7 +8,7 @@ import ctypes as C
 import numpy as np
 
 from . import _lib
-from ._lib import check, NORMALISER_LU_REF, LAYOUT_TALL
+from ._lib import check, NORMALISER_LU_REF, LAYOUT_TALL, LAYOUT_COLMAJOR
 from .core import DeviceMatrix, as_operator, _pd
 
 
@@ -26,13 +26,17 @@ def _negative_iterations(q):
 
 
 def rangefinder(A, l=None, numiterations=None, *, epsilon=1e-8, r=10, Omega=None, omegas=None, rng=None,
-                normaliser=NORMALISER_LU_REF, maxvec=None):
+                normaliser=NORMALISER_LU_REF, maxvec=None, block=None):
     """rangefinder(A, l, numiterations)   -- fixed rank     (src/RandMatFact.jl:50-80)
-    rangefinder(A; epsilon=1e-8, r=10) -- adaptive (4.2)   (src/RandMatFact.jl:15-48)"""
+    rangefinder(A; epsilon=1e-8, r=10) -- adaptive (4.2)   (src/RandMatFact.jl:15-48)
+    rangefinder(A; epsilon, block=b)   -- OPT-IN blocked adaptive finder (not the parity mode: one
+                                          GEMM pass over A per b vectors, see gsi_rangefinder_adaptive_blocked)"""
     op = as_operator(A)
     ctx = op.ctx
     m, n = op.shape
     rng = _rng(rng)
+    if l is None and block is not None:
+        return _rangefinder_adaptive_blocked(op, epsilon, int(block), omegas, rng, maxvec)
     if l is None:
         return _rangefinder_adaptive(op, epsilon, r, Omega, omegas, rng, maxvec)
     if numiterations is None:
@@ -51,25 +55,53 @@ def rangefinder(A, l=None, numiterations=None, *, epsilon=1e-8, r=10, Omega=None
     return out
 
 
+def _wide(ctx, a):
+    """n x c host matrix -> device: TALL up to 256 columns, COLMAJOR beyond (any width)."""
+    a = np.asarray(a, dtype=np.float64)
+    return DeviceMatrix.from_host(ctx, a, LAYOUT_TALL if a.shape[1] <= 256 else LAYOUT_COLMAJOR)
+
+
 def _rangefinder_adaptive(op, epsilon, r, Omega0, omegas, rng, maxvec):
+    """The reference draws its vectors one by one for as long as it needs them (:36); here `maxvec` of
+    them (default min(m, n), the most the algorithm can ever use) are drawn up front, in the
+    reference's order of use, and uploaded as one matrix."""
     ctx = op.ctx
     m, n = op.shape
-    if maxvec is None:
-        maxvec = min(m, n)
     if Omega0 is None:
         Omega0 = rng.standard_normal((n, r))
     if omegas is None:
+        if maxvec is None:
+            maxvec = min(m, n)
         omegas = rng.standard_normal((n, maxvec))
     maxvec = omegas.shape[1]
     O0 = DeviceMatrix.from_host(ctx, Omega0)
-    Os = DeviceMatrix.from_host(ctx, omegas)
-    Q = DeviceMatrix(ctx, m, maxvec, LAYOUT_TALL)
+    Os = _wide(ctx, omegas)
+    Q = DeviceMatrix(ctx, m, maxvec, Os.layout)
     j = C.c_int64()
     try:
         check(ctx._lib.gsi_rangefinder_adaptive(op._h, O0._h, Os._h, float(epsilon), int(r), Q._h, C.byref(j)))
         out = Q.numpy()[:, :j.value].copy()
     finally:
         O0.free(); Os.free(); Q.free()
+    return out
+
+
+def _rangefinder_adaptive_blocked(op, epsilon, block, omegas, rng, maxvec):
+    ctx = op.ctx
+    m, n = op.shape
+    if omegas is None:
+        if maxvec is None:
+            maxvec = min(m, n)
+        omegas = rng.standard_normal((n, maxvec))
+    maxvec = omegas.shape[1]
+    Os = _wide(ctx, omegas)
+    Q = DeviceMatrix(ctx, m, maxvec, Os.layout)
+    j = C.c_int64()
+    try:
+        check(ctx._lib.gsi_rangefinder_adaptive_blocked(op._h, Os._h, float(epsilon), int(block), Q._h, C.byref(j)))
+        out = Q.numpy()[:, :j.value].copy()
+    finally:
+        Os.free(); Q.free()
     return out
 
 

@@ -189,11 +189,22 @@ int32_t gsi_rangefinder_fixed(gsi_op* op, const gsi_buf* Omega, int64_t q, int32
 int32_t gsi_randsvd(gsi_op* op, const gsi_buf* Omega, int64_t K, int64_t p, int64_t q,
                     int32_t normaliser, gsi_buf* Z_out, double* S_host);
 /* rangefinder(A; epsilon, r) (src/RandMatFact.jl:15-48), dense square A, 1 GPU.
- * Omega0: TALL n x r replaces randn(n, r) (:20); omegas: TALL n x maxvec, column t
- * replaces the t-th randn!(omega) (:36).  Q_out: TALL n x maxvec; *j_out = basis size.
+ * Omega0: TALL n x r replaces randn(n, r) (:20); omegas: n x maxvec, column t replaces
+ * the t-th randn!(omega) (:36).  Q_out: n x maxvec; *j_out = basis size (columns beyond
+ * it are zero).  omegas and Q_out may be TALL (maxvec <= 256) or COLMAJOR (any maxvec,
+ * e.g. the reference's implicit bound min(m, n)).
  * Returns GSI_ERR_NO_CONVERGENCE if maxvec vectors did not reach epsilon.             */
 int32_t gsi_rangefinder_adaptive(gsi_op* op, const gsi_buf* Omega0, const gsi_buf* omegas,
                                  double epsilon, int64_t r, gsi_buf* Q_out, int64_t* j_out);
+/* OPT-IN blocked variant of the adaptive range finder (no reference counterpart; NOT the
+ * parity mode): the random vectors are consumed `block` (<= 256) at a time, so A is read
+ * once per block by a tensor-core GEMM instead of once per vector, the block is projected
+ * against the basis (block Gram-Schmidt, twice) and orthonormalised by Householder QR; the
+ * reference's stopping estimator (:26) is evaluated on the block's fresh probes.  Same
+ * error bound, basis size rounded up to the block, different basis than the reference's.
+ * omegas / Q_out as above (TALL or COLMAJOR, n x maxvec).                               */
+int32_t gsi_rangefinder_adaptive_blocked(gsi_op* op, const gsi_buf* omegas, double epsilon, int64_t block,
+                                         gsi_buf* Q_out, int64_t* j_out);
 /* eig_nystrom(A, Q) (src/RandMatFact.jl:92-102): U_out TALL n x l, Sigma_host l.      */
 int32_t gsi_eig_nystrom(gsi_op* op, const gsi_buf* Q, gsi_buf* U_out, double* Sigma_host);
 

@@ -29,7 +29,7 @@ PARITY PINNING STATUS
     defaults: at 1e-8 "parity unpinned" (only pinned by the reference's 2e-2
     end-to-end tests).
 """
-from .randmatfact import (colnorms, rangefinder_adaptive, rangefinder_fixed,
+from .randmatfact import (colnorms, rangefinder_adaptive, rangefinder_adaptive_blocked, rangefinder_fixed,
                           randsvd, eig_nystrom, lu_L_unpermuted)
 from .lowrank import LowRankCovMatrix, PCGALowRankMatrix
 from .lsqr import lsqr

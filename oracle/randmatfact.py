@@ -134,6 +134,36 @@ def rangefinder_adaptive(A, Omega0, omegas, epsilon=1e-8, r=10):
     return Qfull[:, :j].copy()                          # :47
 
 
+def rangefinder_adaptive_blocked(A, omegas, epsilon=1e-8, block=16):
+    """NO REFERENCE COUNTERPART: CPU statement of the product's opt-in blocked adaptive range
+    finder (gsi_rangefinder_adaptive_blocked) -- Halko et al. Alg 4.2 with the
+    random vectors consumed `block` at a time: Y = A Omega_b, block Gram-Schmidt against the basis
+    (twice), the reference's stopping estimator (src/RandMatFact.jl:26) on the block's fresh
+    probes, Householder QR of the block, one more projection + QR of the orthonormalised block.
+    Test infrastructure for that mode only."""
+    A = np.asarray(A, dtype=np.float64)
+    m, n = A.shape
+    thresh = epsilon / np.sqrt(200 / np.pi)
+    Q = np.zeros((m, 0))
+    j = 0
+    while True:
+        b = min(block, omegas.shape[1] - j)
+        if b <= 0:
+            raise IndexError("adaptive rangefinder: maxvec basis vectors did not reach epsilon")
+        Y = A @ omegas[:, j:j + b]
+        for _ in range(2):
+            Y = Y - Q @ (Q.T @ Y)
+        if not np.max(colnorms(Y)) > thresh:
+            break
+        Qb, _ = np.linalg.qr(Y)
+        # a block that overshoots the rank has columns of pure rounding noise, whose "directions" are
+        # not orthogonal to the basis: project the orthonormalised block once more and re-orthonormalise
+        Qb, _ = np.linalg.qr(Qb - Q @ (Q.T @ Qb))
+        Q = np.hstack([Q, Qb])
+        j += b
+    return Q
+
+
 def eig_nystrom(A, Q):
     """src/RandMatFact.jl:92-102 (Halko et al. Alg 5.5). Returns (U, Sigmavec)."""
     B1 = A @ Q                                          # :93

@@ -28,6 +28,45 @@ def test_rangefinder_adaptive(gsi, n, m):
     assert np.linalg.norm(Qo - Q @ (Q.T @ Qo), 2) < 1e-8
 
 
+def test_rangefinder_adaptive_wide(gsi):
+    """the default call (maxvec = min(m, n) > 256 random vectors, COLMAJOR device buffers)
+    on an operator with n > 256, parity with the oracle on identical vectors."""
+    n, m = 600, 40
+    rng = np.random.default_rng(77)
+    A = makeA(rng, n, m)
+    Om0, oms = rng.standard_normal((n, 10)), rng.standard_normal((n, n))
+    Q = gsi.rangefinder(A, Omega=Om0, omegas=oms)
+    assert abs(Q.shape[1] - m) <= 1
+    assert np.linalg.norm(A - Q @ Q.T @ A) < 1e-8 * np.linalg.norm(A)
+    Qo = oracle.rangefinder_adaptive(A, Om0, oms)
+    assert Q.shape == Qo.shape
+    assert np.linalg.norm(Qo - Q @ (Q.T @ Qo), 2) < 1e-8
+    Q2 = gsi.rangefinder(A, rng=np.random.default_rng(1))          # vectors drawn inside, default maxvec
+    assert abs(Q2.shape[1] - m) <= 1 and np.linalg.norm(A - Q2 @ Q2.T @ A) < 1e-8 * np.linalg.norm(A)
+
+
+@pytest.mark.parametrize("n,m,block", [(100, 10, 4), (600, 40, 16), (3000, 120, 32), (1000, 300, 64)])
+def test_rangefinder_adaptive_blocked(gsi, n, m, block):
+    """the opt-in blocked adaptive range finder meets the reference's own acceptance
+    test (test/testrmf.jl:13-15: ||A - QQ'A|| < 1e-8-ish, size ~ rank) with the basis size rounded
+    up to the block, and spans the same subspace as its CPU statement on identical vectors."""
+    rng = np.random.default_rng(n + m + block)
+    A = makeA(rng, n, m)
+    oms = rng.standard_normal((n, min(n, m + 4 * block)))
+    Q = gsi.rangefinder(A, omegas=oms, block=block)
+    assert m <= Q.shape[1] < m + 2 * block and Q.shape[1] % block == 0
+    assert np.max(np.abs(Q.T @ Q - np.eye(Q.shape[1]))) < 1e-12
+    assert np.linalg.norm(A - Q @ (Q.T @ A)) < 1e-8 * np.linalg.norm(A)
+    Qo = oracle.rangefinder_adaptive_blocked(A, oms, block=block)
+    assert Qo.shape == Q.shape
+    # the first ceil(m / block) - 1 blocks are well conditioned: same subspace as the CPU statement
+    lead = (m // block) * block if m % block else m - block
+    if lead > 0:
+        assert np.linalg.norm(Qo[:, :lead] - Q @ (Q.T @ Qo[:, :lead]), 2) < 1e-8
+    with pytest.raises(gsi.GsiError):
+        gsi.rangefinder(A, omegas=oms[:, :block], block=block)      # not enough vectors: NO_CONVERGENCE
+
+
 def test_eig_nystrom_known_answer(gsi):
     # test/testrmf.jl:21-29: eigenvalues 2, 2 +- sqrt(2)
     rng = np.random.default_rng(7)
