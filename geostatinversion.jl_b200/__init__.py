@@ -14,4 +14,6 @@ from .core import (Context, DeviceMatrix, DenseMatrix, LowRankCovMatrix, KernelC
 from . import randmatfact as RandMatFact
 from .randmatfact import randsvd, rangefinder, eig_nystrom
 from . import dist
+from . import fftrf as FFTRF
+from .fftrf import PowerLawFieldSampler
 from .pcga import (getxis, pcgalsqr, pcgadirect, pcga, rga, PCGALowRankMatrix, lu_L, qr_thinQ, svd_small)

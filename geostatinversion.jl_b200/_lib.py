@@ -76,6 +76,7 @@ SIGNATURES = {
     "gsi_rangefinder_adaptive": (_i32, [_p, _p, _p, _f64, _i64, _p, _pi64]),
     "gsi_rangefinder_adaptive_blocked": (_i32, [_p, _p, _f64, _i64, _p, _pi64]),
     "gsi_eig_nystrom": (_i32, [_p, _p, _p, _pd]),
+    "gsi_fftrf_powerlaw": (_i32, [_p, _i32, _pi64, _f64, _f64, _f64, _p, _p]),
     "gsi_pcga_lowrank_matvec": (_i32, [_p, _i64, _i64, _pd, _i64, _pd, _pd, _pd, _i64, _pd, _pd]),
     "gsi_pcga_lsqr_solve": (_i32, [_p, _i64, _i64, _pd, _i64, _pd, _pd, _pd, _i64, _pd, _f64, _f64, _f64,
                                    _i64, _pd, _pi64, _pi32]),

@@ -308,6 +308,20 @@ class LowRankCovMatrix(_Operator):
         self.row0, self.mloc = 0, S.shape[0]
         check(self._lib.gsi_op_lowrankcov(self.ctx._h, self._buf._h, 1 if remove_mean else 0, C.byref(self._h)))
 
+    @classmethod
+    def from_device(cls, samples, remove_mean=True):
+        """Wrap an n x N COLMAJOR DeviceMatrix of sample fields that is already on the device (e.g. from
+        FFTRF.sample_fields_device); the operator takes the buffer over (its mean is removed in place)."""
+        if samples.layout != LAYOUT_COLMAJOR:
+            raise ValueError("LowRankCovMatrix.from_device needs a COLMAJOR DeviceMatrix (n x N)")
+        self = cls.__new__(cls)
+        _Operator.__init__(self, samples.ctx)
+        self.nsamples = samples.shape[1]
+        self._buf = samples
+        self.row0, self.mloc = 0, samples.shape[0]
+        check(self._lib.gsi_op_lowrankcov(self.ctx._h, samples._h, 1 if remove_mean else 0, C.byref(self._h)))
+        return self
+
 
 class KernelCovMatrix(_Operator):
     """Matrix-free covariance operator C[i,j] = sigma2*k(|(x_i-x_j)./ell|) + nugget*(i==j)

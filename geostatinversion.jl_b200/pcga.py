@@ -68,8 +68,16 @@ def getxis(Q, *args, ctx=None, rng=None, Omega=None, normaliser=NORMALISER_LU_RE
         numfields, numxis, p = args[0], args[1], args[2]
         q = args[3] if len(args) > 3 else 3
         seed = args[4] if len(args) > 4 else None
-        fields = [np.asarray(Q(), dtype=np.float64) for _ in range(numfields)]     # rpmap(i->samplefield())
-        A = LowRankCovMatrix(fields, ctx=ctx)
+        if hasattr(Q, "sample_device"):
+            # device sampler (FFTRF.PowerLawFieldSampler): the fields never visit the host
+            Sd = Q.sample_device(numfields)
+            if want_fields:                                                        # before the mean is removed in place
+                Sh = Sd.numpy()
+                fields = [np.ascontiguousarray(Sh[:, i]) for i in range(Sh.shape[1])]
+            A = LowRankCovMatrix.from_device(Sd)
+        else:
+            fields = [np.asarray(Q(), dtype=np.float64) for _ in range(numfields)]     # rpmap(i->samplefield())
+            A = LowRankCovMatrix(fields, ctx=ctx)
     else:
         numxis, p = args[0], args[1]
         q = args[2] if len(args) > 2 else 3

@@ -208,6 +208,15 @@ int32_t gsi_rangefinder_adaptive_blocked(gsi_op* op, const gsi_buf* omegas, doub
 /* eig_nystrom(A, Q) (src/RandMatFact.jl:92-102): U_out TALL n x l, Sigma_host l.      */
 int32_t gsi_eig_nystrom(gsi_op* op, const gsi_buf* Q, gsi_buf* U_out, double* Sigma_host);
 
+/* FFTRF.powerlaw_structuredgrid (src/FFTRF.jl:83-100) for a batch of fields, on the device -- the
+ * sampler behind getxis(samplefield, numfields, ...) (src/GeostatInversion.jl:29-38).  dim in {2, 3};
+ * Ns[dim] grid sizes (each <= 1024).  phi: COLMAJOR prod(2*Ns) x nfields, column f = the `randn(size(S))`
+ * of field f (:75) in Julia's linear order of the (2 Ns[2], 2 Ns[1] [, 2 Ns[3]]) array (:45,52).
+ * samples: COLMAJOR prod(Ns) x nfields, column f = vec(field f) (mean k0, corrected std dk) -- ready for
+ * gsi_op_lowrankcov without a host round trip.                                                    */
+int32_t gsi_fftrf_powerlaw(gsi_ctx* ctx, int32_t dim, const int64_t* Ns, double k0, double dk, double beta,
+                           const gsi_buf* phi, gsi_buf* samples);
+
 /* ---- PCGA helpers (src/lsqr.jl:35-63, src/lowrank.jl:83-97, GeostatInversion.jl:101-103) */
 /* v = [R xs + E (E' xs) + HX x_end ; HX . xs]  (PCGALowRankMatrix mul!, lowrank.jl:83-97)
  * E: host nobs x K col-major (columns = etas), HX: nobs, Rdiag: nobs (diagonal R) or

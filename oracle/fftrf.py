@@ -12,7 +12,7 @@ def _fouriercoords(N):
     return np.concatenate([np.arange(0, N + 1), -np.arange(N - 1, 0, -1)]).astype(np.float64)
 
 
-def powerlaw_structuredgrid(Ns, k0, dk, beta, rng):
+def powerlaw_structuredgrid(Ns, k0, dk, beta, rng=None, phi=None):
     Ns = list(Ns)
     d = len(Ns)
     fc = [_fouriercoords(N) for N in Ns]
@@ -29,7 +29,9 @@ def powerlaw_structuredgrid(Ns, k0, dk, beta, rng):
     with np.errstate(divide="ignore"):
         S = S ** (0.25 * beta)                                   # :64
     S[np.isinf(S)] = 0.0                                         # :65-67
-    phi = rng.standard_normal(S.shape)                           # :75
+    if phi is None:
+        phi = rng.standard_normal(S.shape)                       # :75
+    assert phi.shape == S.shape
     result = S * (np.cos(2 * np.pi * phi) + 1j * np.sin(2 * np.pi * phi))  # :77-79 cospi/sinpi
     kc = np.fft.ifftn(result)                                    # :92
     # reducek :9-38 -- finalk[j, i(, h)] = real(k[i, j(, h)]) over the first halves

@@ -248,3 +248,43 @@ def test_kernelcov_sweep_window(gsi, table):
         ctx.set_option("kcov.sweep_groups", 3)
     with pytest.raises(gsi.GsiError):
         ctx.set_option("no.such.option", 1)
+
+
+# ---------------------------------------------------------------- device FFTRF
+@pytest.mark.parametrize("Ns", [(28, 37), (64, 32), (25, 50), (13, 17, 11), (32, 16, 8), (27, 31, 26)])
+def test_fftrf_powerlaw_structuredgrid(gsi, Ns):
+    """test/testfftrf.jl:6-15 (mean == k0, std == dk, size == Ns) and parity of the device sampler
+    (direct DFT over the surviving outputs) with the oracle restatement of src/FFTRF.jl:83-100
+    (FFT of the doubled grid) on identical phases."""
+    from oracle.fftrf import powerlaw_structuredgrid as ref
+    rng = np.random.default_rng(sum(Ns))
+    k0, dk, beta = rng.standard_normal(), rng.random() + 0.1, -2 - rng.random()
+    shape = gsi.FFTRF._doubled_shape(Ns)
+    phi = rng.standard_normal(shape)
+    k = gsi.FFTRF.powerlaw_structuredgrid(Ns, k0, dk, beta, phi=phi)
+    assert list(k.shape) == list(Ns)
+    assert abs(np.mean(k) - k0) < 1e-12 * max(1.0, abs(k0)) + 1e-12
+    assert abs(np.std(k, ddof=1) - dk) < 1e-12
+    kr = ref(list(Ns), k0, dk, beta, phi=phi)
+    assert relerr(k, kr) < 1e-11
+
+
+def test_getxis_device_sampler_matches_host_fields(gsi):
+    """getxis(samplefield, numfields, numxis, p, q): the device sampler path (fields generated and kept on
+    the device) returns the same fields and the same xis as handing the SAME fields to the host-list path
+    (src/GeostatInversion.jl:29-38, 58-61)."""
+    Ns, nf, K, p = (40, 36), 24, 8, 4
+    n = Ns[0] * Ns[1]
+    Omega = np.random.default_rng(1).standard_normal((n, K + p))
+    sampler = gsi.PowerLawFieldSampler(Ns, 2.0, 3.14, -3.5, rng=11)
+    xis, fields = gsi.getxis(sampler, nf, K, p, 3, Omega=Omega, want_fields=True)
+    assert len(fields) == nf and len(xis) == K and fields[0].shape == (n,)
+    it = iter(fields)
+    xis_host = gsi.getxis(lambda: next(it), nf, K, p, 3, Omega=Omega)
+    for a, b in zip(xis, xis_host):
+        assert min(np.linalg.norm(a - b), np.linalg.norm(a + b)) / np.linalg.norm(b) < 1e-10
+    # the same phases through the oracle's FFT
+    from oracle.fftrf import powerlaw_structuredgrid as ref
+    rng = np.random.default_rng(11)
+    phi = rng.standard_normal((nf,) + gsi.FFTRF._doubled_shape(Ns))
+    assert relerr(fields[3], ref(list(Ns), 2.0, 3.14, -3.5, phi=phi[3]).ravel(order="F")) < 1e-11
