@@ -31,7 +31,26 @@ import sys
 # The CPU arms (oracle on SciPy/OpenBLAS) must see the same BLAS thread count whatever launched
 # this process: torch.distributed.run exports OMP_NUM_THREADS=1, which made the round-1 reference
 # arm 5.6x slower at N >= 2 than at N = 1.  Pin before NumPy loads OpenBLAS.
-_NCPU = os.cpu_count() or 1
+def _usable_cpus():
+    """Cores this process may really use: the affinity mask, capped by a cgroup CPU quota if one is set
+    (a container can see more cores than it is allowed to run on; oversubscribing them with BLAS
+    threads makes the CPU arm several times slower)."""
+    n = os.cpu_count() or 1
+    try:
+        n = min(n, len(os.sched_getaffinity(0)))
+    except Exception:
+        pass
+    try:
+        with open("/sys/fs/cgroup/cpu.max") as f:
+            quota, period = f.read().split()[:2]
+        if quota != "max":
+            n = max(1, min(n, int(float(quota) / float(period))))
+    except Exception:
+        pass
+    return n
+
+
+_NCPU = _usable_cpus()
 for _v in ("OMP_NUM_THREADS", "OPENBLAS_NUM_THREADS", "MKL_NUM_THREADS"):
     os.environ[_v] = str(_NCPU)
 

@@ -261,13 +261,22 @@ end
 rangefinder(A; epsilon=1e-8, r=10) -- reference src/RandMatFact.jl:15-48 (HMT algorithm 4.2).
 The r start vectors (`randn(n, r)`, :20) and the vectors the reference draws one by one with
 `randn!(omega)` (:36) are drawn here in the same order and handed to the library in blocks of
-`chunk` columns, so a run consumes the same random stream as the reference up to the point
-where it stops (the reference draws nothing after convergence; this shim draws to the end of
-the current block).
+one matrix, so a run consumes the same random stream as the reference up to the point where it
+stops (the reference draws nothing after convergence; this shim draws
+the whole set of min(m, n) vectors up front).
 """
-function rangefinder(A; epsilon::Float64=1e-8, r::Int=10, chunk::Int=64)
+function rangefinder(A; epsilon::Float64=1e-8, r::Int=10, block::Union{Nothing, Int}=nothing)
 	op = asoperator(A)
 	m, n = size(op)
+	if block !== nothing                                 # OPT-IN blocked finder (not the parity mode): one GEMM pass over A per block
+		maxvec = min(m, n)
+		oms = upload!(DeviceMatrix(op.ctx, GSI_LAYOUT_COLMAJOR, n, maxvec), randn(n, maxvec))
+		Q = DeviceMatrix(op.ctx, GSI_LAYOUT_COLMAJOR, m, maxvec)
+		j = Ref{Int64}(0)
+		check(ccall((:gsi_rangefinder_adaptive_blocked, LIB), Int32, (Ptr{Cvoid}, Ptr{Cvoid}, Float64, Int64, Ptr{Cvoid}, Ref{Int64}),
+			op.h, oms.h, epsilon, block, Q.h, j))
+		return download(Q)[:, 1:j[]]
+	end
 	Om0 = upload!(DeviceMatrix(op.ctx, GSI_LAYOUT_TALL, n, r), randn(n, r))
 	maxvec = min(m, n)
 	oms = upload!(DeviceMatrix(op.ctx, GSI_LAYOUT_COLMAJOR, n, maxvec), randn(n, maxvec))
@@ -289,6 +298,46 @@ function eig_nystrom(A, Q::Matrix{Float64})
 	return download(U), Sigmavec
 end
 end # RandMatFact
+
+"""
+FFTRF.powerlaw_structuredgrid (src/FFTRF.jl:83-100) on the device, for a batch of fields: the phases
+`randn(size(S))` (:75) are drawn here, per field, in the reference's order; the fields stay on the
+device as the columns of an n x numfields matrix (gsi_fftrf_powerlaw).
+"""
+module FFTRF
+import ..GeostatInversionB200: LIB, check, context, Context, DeviceMatrix, upload!, download, GSI_LAYOUT_COLMAJOR
+
+doubledsize(Ns::Vector{Int}) = length(Ns) == 2 ? (2 * Ns[2], 2 * Ns[1]) : (2 * Ns[2], 2 * Ns[1], 2 * Ns[3])   # size(S), :45,52
+
+function samplefieldsdevice(Ns::Vector{Int}, k0::Number, dk::Number, beta::Number, numfields::Int; ctx::Context=context())
+	(length(Ns) == 2 || length(Ns) == 3) || error("unsupported dimension: $(length(Ns))")
+	big = prod(doubledsize(Ns))
+	phi = Matrix{Float64}(undef, big, numfields)
+	for f = 1:numfields
+		phi[:, f] = vec(randn(doubledsize(Ns)))              # mulbyphi, :74-75
+	end
+	phid = upload!(DeviceMatrix(ctx, GSI_LAYOUT_COLMAJOR, big, numfields), phi)
+	out = DeviceMatrix(ctx, GSI_LAYOUT_COLMAJOR, prod(Ns), numfields)
+	Ns64 = Int64.(Ns)
+	GC.@preserve Ns64 check(ccall((:gsi_fftrf_powerlaw, LIB), Int32,
+		(Ptr{Cvoid}, Int32, Ptr{Int64}, Float64, Float64, Float64, Ptr{Cvoid}, Ptr{Cvoid}),
+		ctx.h, length(Ns), Ns64, k0, dk, beta, phid.h, out.h))
+	return out
+end
+
+"powerlaw_structuredgrid(Ns, k0, dk, beta) -> Array of size Ns (src/FFTRF.jl:83-100)"
+powerlaw_structuredgrid(Ns::Vector, k0::Number, dk::Number, beta::Number) =
+	reshape(download(samplefieldsdevice(Vector{Int}(Ns), k0, dk, beta, 1))[:, 1], Ns...)
+
+"a `samplefield` that getxis recognises and evaluates as ONE batch on the device"
+struct PowerLawSampler
+	Ns::Vector{Int}
+	k0::Float64
+	dk::Float64
+	beta::Float64
+end
+(s::PowerLawSampler)() = vec(powerlaw_structuredgrid(s.Ns, s.k0, s.dk, s.beta))
+end # FFTRF
 
 function randsvdwithseed(Q, numxis, p, q, seed::Nothing)
 	return RandMatFact.randsvd(Q, numxis, p, q)
@@ -315,6 +364,21 @@ function getxis(::Type{Val{:iwantfields}}, samplefield::Function, numfields::Int
 	end
 	return xis, fields
 end
+
+"getxis for the device sampler: fields generated, mean-removed and factored without leaving the device"
+function getxis(::Type{Val{:iwantfields}}, sampler::FFTRF.PowerLawSampler, numfields::Int, numxis::Int, p::Int, q::Int=3, seed=nothing)
+	ctx = context()
+	Sd = FFTRF.samplefieldsdevice(sampler.Ns, sampler.k0, sampler.dk, sampler.beta, numfields; ctx=ctx)
+	S = download(Sd)                                     # the raw fields the reference also returns (before mean removal)
+	out = Ref{Ptr{Cvoid}}(C_NULL)
+	check(ccall((:gsi_op_lowrankcov, LIB), Int32, (Ptr{Cvoid}, Ptr{Cvoid}, Int32, Ref{Ptr{Cvoid}}), ctx.h, Sd.h, 1, out))
+	lrcm = LowRankCovMatrix(out[], Sd, ctx, 1:Sd.rows)
+	finalizer(freeop, lrcm)
+	Z = randsvdwithseed(lrcm, numxis, p, q, seed)
+	return [Z[:, i] for i = 1:numxis], [S[:, i] for i = 1:numfields]
+end
+getxis(sampler::FFTRF.PowerLawSampler, numfields::Int, numxis::Int, p::Int, q::Int=3, seed=nothing) =
+	getxis(Val{:iwantfields}, sampler, numfields, numxis, p, q, seed)[1]
 
 "getxis(samplefield, numfields, numxis, p, q=3, seed=nothing) -- src/GeostatInversion.jl:58-61"
 function getxis(samplefield::Function, numfields::Int, numxis::Int, p::Int, q::Int=3, seed=nothing)
