@@ -8,7 +8,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libgsi_b200.so")
+LIB_PATH = os.environ.get("GSI_B200_LIB") or os.path.join(_HERE, "lib", "libgsi_b200.so")   # same override as the Julia shim
 
 # status codes (include/gsi_b200.h)
 OK = 0

@@ -81,22 +81,33 @@ dense_gemm_kernel(const __grid_constant__ CUtensorMap amap, const __grid_constan
 
     const int64_t total_it = my_rounds * nkt;
     const int lookahead = nstages > 2 ? nstages - 2 : 1;
-    auto produce = [&](int64_t nxt) {
-        const int s = (int)(nxt % nstages);
-        const uint32_t ph = (uint32_t)((nxt / nstages) & 1);
-        const int64_t kt = nxt % nkt;
+    // producer state, advanced incrementally (no 64-bit divisions on thread 0's path -- its warp is an MMA warp too)
+    int64_t p_it = 0, p_kt = 0, p_round = 0, p_row = 0;
+    int p_s = 0;
+    uint32_t p_ph = 0;
+    {
         int nact_unused;
-        const int64_t row = round_base(nxt / nkt, nact_unused) * 16;        // first output row of the tile
-        mbar_wait(&empty[s], ph ^ 1u);
-        double* xs = smem + (size_t)s * stage_doubles;
+        if (my_rounds > 0) p_row = round_base(0, nact_unused) * 16;       // first output row of the tile
+    }
+    auto produce_next = [&]() {
+        mbar_wait(&empty[p_s], p_ph ^ 1u);
+        double* xs = smem + (size_t)p_s * stage_doubles;
         double* as = xs + DG_BK * ld;
-        mbar_expect_tx(&full[s], stage_bytes);
-        bulk_g2s(xs, p.X + kt * DG_BK * p.ld, DG_BK * ld * 8, &full[s]);
-        if (TRANS) tma_load_2d(as, &amap, (int)(kt * DG_BK), (int)row, &full[s]);
-        else       tma_load_2d(as, &amap, (int)row, (int)(kt * DG_BK), &full[s]);
+        mbar_expect_tx(&full[p_s], stage_bytes);
+        bulk_g2s(xs, p.X + p_kt * DG_BK * p.ld, DG_BK * ld * 8, &full[p_s]);
+        if (TRANS) tma_load_2d(as, &amap, (int)(p_kt * DG_BK), (int)p_row, &full[p_s]);
+        else       tma_load_2d(as, &amap, (int)p_row, (int)(p_kt * DG_BK), &full[p_s]);
+        ++p_it;
+        if (++p_kt == nkt) {
+            p_kt = 0;
+            ++p_round;
+            int nact_unused;
+            if (p_round < my_rounds) p_row = round_base(p_round, nact_unused) * 16;
+        }
+        if (++p_s == nstages) { p_s = 0; p_ph ^= 1u; }
     };
     if (tid == 0) {
-        for (int64_t i = 0; i < lookahead && i < total_it; ++i) produce(i);
+        for (int64_t i = 0; i < lookahead && i < total_it; ++i) produce_next();
     }
 
     const int g = lane >> 2, t = lane & 3;
@@ -104,7 +115,8 @@ dense_gemm_kernel(const __grid_constant__ CUtensorMap amap, const __grid_constan
     const int rg = warp >> 2;
     const int cg = (warp + rg) & 3;
     const int nb0 = cg * NBW;
-    int64_t it = 0;
+    int c_s = 0;                       // consumer pipeline stage / mbarrier phase
+    uint32_t c_ph = 0;
     for (int64_t round = 0; round < my_rounds; ++round) {
         int nact = 0;
         const int64_t base_rg = round_base(round, nact);
@@ -114,11 +126,11 @@ dense_gemm_kernel(const __grid_constant__ CUtensorMap amap, const __grid_constan
         for (int h = 0; h < 2; ++h)
 #pragma unroll
             for (int nb = 0; nb < NBW; ++nb) { acc[h][nb][0] = 0.0; acc[h][nb][1] = 0.0; }
-        for (int64_t kt = 0; kt < nkt; ++kt, ++it) {
-            if (tid == 0 && it + lookahead < total_it) produce(it + lookahead);
-            const int s = (int)(it % nstages);
-            const uint32_t ph = (uint32_t)((it / nstages) & 1);
-            mbar_wait(&full[s], ph);
+        for (int64_t kt = 0; kt < nkt; ++kt) {
+            if (tid == 0 && p_it < total_it) produce_next();
+            const int s = c_s;
+            mbar_wait(&full[s], c_ph);
+            if (++c_s == nstages) { c_s = 0; c_ph ^= 1u; }
             __syncwarp();
             const double* xs = smem + (size_t)s * stage_doubles;
             const double* as = xs + DG_BK * ld;

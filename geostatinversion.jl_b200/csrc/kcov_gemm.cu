@@ -53,6 +53,10 @@ struct KcovParams {
     int64_t ld, ldw;
     double sigma2, nugget, beta;
     int stages;
+    // stream-K tail (see the schedule comment in the kernel): the 64-row tiles left over after the full rounds
+    // are split along k into equal shares of tail_u k-tiles per CTA; partial sums go to `partial`
+    int64_t tail_u;        // k-tiles of tail work per CTA (0: no tail)
+    double* partial;       // [2 * grid][KC_BM][ldw] raw accumulators of the tail segments (slot 2b + s)
 };
 
 // 2^(j/64), j = 0..63, correctly rounded (generated with 200-bit arithmetic)
@@ -175,26 +179,21 @@ __global__ void __launch_bounds__(KC_THREADS, 1) kcov_gemm_kernel(const __grid_c
     }
     __syncthreads();
 
-    // Work schedule.  Full rounds: CTA b takes the 64-row tile (round*grid + b), i.e. four
-    // consecutive 16-row groups.  The remaining (< 4*grid) row groups form ONE tail round
-    // spread over all CTAs, q = ceil(remaining/grid) groups each: a CTA with a single
-    // active row group finishes its k-sweep in ~0.4 of a full tile's time (its 4 warps are
-    // DMMA-issue-bound, not pipe-bound), which removes most of the wave-quantisation tail.
+    // Work schedule.  Full rounds: CTA b takes the 64-row tile (round*grid + b), i.e. four consecutive
+    // 16-row groups, and sweeps all nkt k-tiles (cyclically, from its own start tile kt0).  The tiles left
+    // over after the full rounds (< grid of them) form the STREAM-K TAIL: their tail_tiles * nkt k-tile
+    // units are cut into equal contiguous shares of p.tail_u units, one share per CTA, so a share is a k
+    // range of one tile or the end of one tile plus the start of the next -- at most two SEGMENTS.  A tail
+    // segment stores its raw accumulators to p.partial (slot 2b + s); kcov_tail_fixup_kernel adds the
+    // pieces of a tile in ascending CTA order (deterministic) and applies sigma2 / nugget.  Every SM thus
+    // ends within one k-tile of every other whatever the row count (round 1 spread the leftover 16-row
+    // groups over the CTAs with full k sweeps: 4.5 % of a C3 product at 8 GPUs, where a rank's 1568 row
+    // groups are 2.65 rounds).
     const int64_t total_rg = (p.mloc + 15) / 16;
     const int64_t per_round = (int64_t)gridDim.x * 4;
     const int64_t full_rounds = total_rg / per_round;
-    const int64_t remaining = total_rg - full_rounds * per_round;
-    const int64_t q_tail = (remaining + gridDim.x - 1) / gridDim.x;          // 0..4
-    const bool has_tail = remaining > 0 && (int64_t)blockIdx.x * q_tail < remaining;
-    const int64_t my_rounds = full_rounds + (has_tail ? 1 : 0);
-    // first row group and number of active row groups of my round j
-    auto round_base = [&](int64_t j, int& nact) -> int64_t {
-        if (j < full_rounds) { nact = 4; return (j * gridDim.x + blockIdx.x) * 4; }
-        const int64_t b0 = (int64_t)blockIdx.x * q_tail;
-        const int64_t left = remaining - b0;
-        nact = (int)(left < q_tail ? left : q_tail);
-        return full_rounds * per_round + b0;
-    };
+    const int64_t tail_rg0 = full_rounds * per_round;                         // first row group of the tail
+    const int64_t tail_tiles = (total_rg - tail_rg0 + 3) / 4;
     const int64_t nkt = (p.n + KC_BK - 1) / KC_BK;
     // De-synchronised (cyclic) k sweeps (gsi_ctx_set_option "kcov.sweep_*" / GSI_SWEEP): CTA b starts
     // its sweep (b mod groups) * separation tiles into X (default 64 groups over a quarter of X).
@@ -222,26 +221,95 @@ __global__ void __launch_bounds__(KC_THREADS, 1) kcov_gemm_kernel(const __grid_c
     // default; the window is the knob for deployments that must spare HBM bandwidth.  Why the
     // L2-served stream costs the DMMA pipe ~13 % is the first ncu question of the next round.
     const int64_t full_it = full_rounds * nkt;
-    const unsigned n_tail_ctas = q_tail > 0 ? (unsigned)((remaining + q_tail - 1) / q_tail) : 0u;
+    // my share of the tail: units [u0, u1) -> segment A = (tile tA, k-tiles [kA, kA + lenA)), segment B = (tile tA + 1, [0, lenB))
+    const int64_t tail_units = tail_tiles * nkt;
+    int64_t u0 = (int64_t)blockIdx.x * p.tail_u, u1 = u0 + p.tail_u;
+    if (u0 > tail_units) u0 = tail_units;
+    if (u1 > tail_units) u1 = tail_units;
+    const int64_t tA = u0 / nkt, kA = u0 - tA * nkt;
+    const int64_t lenA = (u1 - u0 < nkt - kA) ? u1 - u0 : nkt - kA;
+    const int64_t lenB = (u1 - u0) - lenA;
+    const int nseg_tail = (lenA > 0 ? 1 : 0) + (lenB > 0 ? 1 : 0);
+    const int64_t nseg = full_rounds + nseg_tail;
+    // segment j: first row group, active row groups, first k-tile, k-tiles, partial slot (-1: direct output)
+    struct Seg { int64_t base_rg; int nact; int64_t kbeg; int64_t klen; int slot; };
+    auto seg_info = [&](int64_t j) -> Seg {
+        Seg g;
+        if (j < full_rounds) { g.base_rg = (j * gridDim.x + blockIdx.x) * 4; g.nact = 4; g.kbeg = 0; g.klen = nkt; g.slot = -1; return g; }
+        const int sidx = (int)(j - full_rounds);
+        const int64_t tile = tA + sidx;
+        g.base_rg = tail_rg0 + tile * 4;
+        const int64_t left = total_rg - g.base_rg;
+        g.nact = (int)(left < 4 ? left : 4);
+        g.kbeg = sidx == 0 ? kA : 0;
+        g.klen = sidx == 0 ? lenA : lenB;
+        g.slot = 2 * (int)blockIdx.x + sidx;
+        return g;
+    };
+    // iteration `it` of this CTA -> its segment and global k-tile
+    auto locate = [&](int64_t it_, int64_t& j, int64_t& kt) {
+        if (it_ < full_it) {
+            j = it_ / nkt;
+            kt = it_ - j * nkt + kt0;
+            if (kt >= nkt) kt -= nkt;
+        } else {
+            const int64_t r = it_ - full_it;
+            if (r < lenA) { j = full_rounds; kt = kA + r; }
+            else { j = full_rounds + 1; kt = r - lenA; }
+        }
+    };
+    // CTAs that execute iteration x of the tail (x >= 0): those whose share is longer than x
+    auto tail_ctas_beyond = [&](int64_t x) -> unsigned {
+        if (p.tail_u <= 0 || x >= p.tail_u) return 0u;
+        int64_t c = (tail_units - x + p.tail_u - 1) / p.tail_u;
+        if (c > (int64_t)gridDim.x) c = gridDim.x;
+        return c < 0 ? 0u : (unsigned)c;
+    };
     bool window_on = p.win_epochs > 0;            // thread 0 only
     const uint64_t xpolicy = l2_policy_evict_last();
     constexpr uint32_t stage_bytes = (uint32_t)(KC_BK * ld * sizeof(double) +
                                                 DIM * KC_BK * (KIND == KC_KIND_TABLE ? sizeof(int) : sizeof(double)));
 
     // ---------------- producer (thread 0): streams X / coordinate tiles ----------------------
-    const int64_t total_it = my_rounds * nkt;
+    const int64_t total_it = full_it + (u1 - u0);
     const int lookahead = nstages > 2 ? nstages - 2 : 1;
-    auto produce = [&](int64_t nxt) {
-        const int s = (int)(nxt % nstages);
-        const uint32_t ph = (uint32_t)((nxt / nstages) & 1);
-        int64_t kt = nxt % nkt + kt0;
-        if (kt >= nkt) kt -= nkt;
-        if (p.win_epochs > 0 && (nxt & (((int64_t)1 << p.epoch_shift) - 1)) == 0) {
-            const int64_t e = nxt >> p.epoch_shift;
+    // Producer state, advanced incrementally (no 64-bit divisions on thread 0's path: its warp is an MMA
+    // warp too, and what the producer spends per k-tile is added to the whole CTA's iteration time):
+    //   p_it     next iteration to produce      p_s / p_ph   its pipeline stage / mbarrier phase
+    //   p_kt     its global k-tile              p_left       k-tiles left in its segment (incl. itself)
+    //   p_seg    its segment (0 .. nseg-1)
+    int64_t p_it = 0, p_kt = 0, p_left = 0, p_seg = -1;
+    int p_s = 0;
+    uint32_t p_ph = 0;
+    // first k-tile and length of segment j
+    auto seg_first_kt = [&](int64_t j, int64_t& len) -> int64_t {
+        if (j < full_rounds) { len = nkt; return kt0; }
+        if (j == full_rounds) { len = lenA; return kA; }
+        len = lenB; return 0;
+    };
+    auto produce_next = [&]() {
+        if (p_left == 0) {                                        // enter the next segment
+            ++p_seg;
+            p_kt = seg_first_kt(p_seg, p_left);
+        }
+        const int64_t kt = p_kt;
+        // k-tile of the iteration after this one (its coordinates ride along with this stage)
+        int64_t ktn;
+        if (p_left > 1) {
+            ktn = kt + 1;
+            if (p_seg < full_rounds && ktn == nkt) ktn = 0;
+        } else if (p_seg + 1 < nseg) {
+            int64_t len_unused;
+            ktn = seg_first_kt(p_seg + 1, len_unused);
+        } else {
+            ktn = kt;
+        }
+        if (p.win_epochs > 0 && (p_it & (((int64_t)1 << p.epoch_shift) - 1)) == 0) {
+            const int64_t e = p_it >> p.epoch_shift;
             atomicAdd(p.sync_cnt + e, 1u);
             const int64_t ew = e - p.win_epochs;
             if (window_on && ew >= 0) {
-                const unsigned target = ((ew << p.epoch_shift) < full_it) ? gridDim.x : n_tail_ctas;
+                const unsigned target = ((ew << p.epoch_shift) < full_it) ? gridDim.x : tail_ctas_beyond((ew << p.epoch_shift) - full_it);
                 const volatile unsigned int* c = p.sync_cnt + ew;
                 const long long t0 = clock64();
                 while (*c < target) {
@@ -249,26 +317,29 @@ __global__ void __launch_bounds__(KC_THREADS, 1) kcov_gemm_kernel(const __grid_c
                 }
             }
         }
-        mbar_wait(&empty[s], ph ^ 1u);
-        double* xs = smem + (size_t)s * stage_doubles;
+        mbar_wait(&empty[p_s], p_ph ^ 1u);
+        double* xs = smem + (size_t)p_s * stage_doubles;
         double* us = xs + KC_BK * ld;
-        mbar_expect_tx(&full[s], stage_bytes);
-        if (p.l2_hint) bulk_g2s_hint(xs, p.X + kt * KC_BK * p.ld, KC_BK * ld * 8, &full[s], xpolicy);
-        else bulk_g2s(xs, p.X + kt * KC_BK * p.ld, KC_BK * ld * 8, &full[s]);
-        const int64_t ktn = (kt + 1 == nkt) ? 0 : kt + 1;      // coordinates of the NEXT k-tile ride along
+        mbar_expect_tx(&full[p_s], stage_bytes);
+        if (p.l2_hint) bulk_g2s_hint(xs, p.X + kt * KC_BK * p.ld, KC_BK * ld * 8, &full[p_s], xpolicy);
+        else bulk_g2s(xs, p.X + kt * KC_BK * p.ld, KC_BK * ld * 8, &full[p_s]);
         if (KIND == KC_KIND_TABLE) {
             int* usi = reinterpret_cast<int*>(us);
             for (int k = 0; k < DIM; ++k)
-                bulk_g2s(usi + k * KC_BK, p.lat + k * p.n_pad + ktn * KC_BK, KC_BK * 4, &full[s]);
+                bulk_g2s(usi + k * KC_BK, p.lat + k * p.n_pad + ktn * KC_BK, KC_BK * 4, &full[p_s]);
         } else {
             for (int k = 0; k < DIM; ++k)
-                bulk_g2s(us + k * KC_BK, p.u + k * p.n_pad + ktn * KC_BK, KC_BK * 8, &full[s]);
+                bulk_g2s(us + k * KC_BK, p.u + k * p.n_pad + ktn * KC_BK, KC_BK * 8, &full[p_s]);
         }
+        // advance
+        ++p_it;
+        --p_left;
+        p_kt = kt + 1;
+        if (p_seg < full_rounds && p_kt == nkt) p_kt = 0;
+        if (++p_s == nstages) { p_s = 0; p_ph ^= 1u; }
     };
     if (tid == 0) {
-        for (int64_t i = 0; i < lookahead && i < total_it; ++i) {
-            produce(i);
-        }
+        for (int64_t i = 0; i < lookahead && i < total_it; ++i) produce_next();
     }
 
     const int g = lane >> 2;      // fragment row (A, C) / column (B)
@@ -316,15 +387,16 @@ __global__ void __launch_bounds__(KC_THREADS, 1) kcov_gemm_kernel(const __grid_c
         dst[1] = make_double2(v[2], v[3]);
     };
 
-    int64_t it = 0;
+    int c_s = 0;                       // consumer pipeline stage / mbarrier phase of iteration `it`
+    uint32_t c_ph = 0;
     double ui[DIM];
-    int nact = 0, nact_next = 0;
-    int64_t base_rg = 0;
-    if (my_rounds > 0) {
-        // prologue: kernel values of (first round, k-tile 0) straight from global coordinates
-        base_rg = round_base(0, nact);
-        row_coords(base_rg, ui);
-        if (rg < nact) {
+    if (nseg > 0) {
+        // prologue: kernel values of (first segment, its first k-tile) straight from global coordinates
+        const Seg g0 = seg_info(0);
+        int64_t j0, ktf;
+        locate(0, j0, ktf);
+        row_coords(g0.base_rg, ui);
+        if (rg < g0.nact) {
             double v[4];
             if (KIND == KC_KIND_TABLE) {
 #pragma unroll
@@ -332,47 +404,58 @@ __global__ void __launch_bounds__(KC_THREADS, 1) kcov_gemm_kernel(const __grid_c
                     int idx = 0;
 #pragma unroll
                     for (int k = DIM - 1; k >= 0; --k) {
-                        int dk = li[k] - p.lat[k * p.n_pad + kt0 * KC_BK + gj0 + e];
+                        int dk = li[k] - p.lat[k * p.n_pad + ktf * KC_BK + gj0 + e];
                         dk = dk < 0 ? -dk : dk;
                         idx = (k == DIM - 1) ? dk : idx * (k == 0 ? p.nx : p.ny) + dk;
                     }
                     v[e] = __ldg(p.table + idx);
                 }
             } else {
-                gen4(ui, p.u + kt0 * KC_BK, p.n_pad, v);
+                gen4(ui, p.u + ktf * KC_BK, p.n_pad, v);
             }
             store4(a_tiles, v);
         }
         __syncwarp();
         if (lane == 0) mbar_arrive(&abar[rg]);
     }
-    for (int64_t round = 0; round < my_rounds; ++round) {
-        if (round > 0) base_rg = round_base(round, nact);
-        const bool active = rg < nact;                                // warp-uniform
-        int64_t base_next = base_rg;
-        nact_next = 0;
-        if (round + 1 < my_rounds) base_next = round_base(round + 1, nact_next);
+    // (loop state is kept small on purpose: the kernel sits at the 128-register limit and every value that
+    //  lives across the k loop costs the generation / MMA interleave its scheduling freedom)
+    int par = 0;                                                      // parity of the A-tile buffer of this iteration
+    for (int64_t j = 0; j < nseg; ++j) {
+        int klen;
+        bool active;
+        {
+            const Seg sg = seg_info(j);
+            klen = (int)sg.klen;
+            active = rg < sg.nact;                                    // warp-uniform
+        }
         double acc[2][NBW][2];
 #pragma unroll
         for (int h = 0; h < 2; ++h)
 #pragma unroll
             for (int nb = 0; nb < NBW; ++nb) { acc[h][nb][0] = 0.0; acc[h][nb][1] = 0.0; }
 
-        for (int64_t kt = 0; kt < nkt; ++kt, ++it) {
-            if (tid == 0 && it + lookahead < total_it) produce(it + lookahead);
-            const int s = (int)(it % nstages);
-            const uint32_t ph = (uint32_t)((it / nstages) & 1);
-            mbar_wait(&full[s], ph);
+        for (int ktl = 0; ktl < klen; ++ktl, par ^= 1) {
+            if (tid == 0 && p_it < total_it) produce_next();           // (p_it == it + lookahead)
+            const int s = c_s;
+            mbar_wait(&full[s], c_ph);
+            if (++c_s == nstages) { c_s = 0; c_ph ^= 1u; }
             __syncwarp();
             const double* xs = smem + (size_t)s * stage_doubles;
-            const double* us = xs + KC_BK * ld;                       // coordinates of k-tile kt+1 (wraps to 0)
-            const double* as = a_tiles + (size_t)(it & 1) * a_doubles;
-            // ---- kernel values of the NEXT k-tile (independent of the MMAs below: the two
+            const double* us = xs + KC_BK * ld;                       // coordinates of the next iteration's k-tile
+            const double* as = a_tiles + (size_t)par * a_doubles;
+            // ---- kernel values of the NEXT iteration's block (independent of the MMAs below: the two
             //      instruction streams overlap on the shared FP64 pipe)
-            const bool last_kt = (kt + 1 == nkt);
-            if (last_kt) row_coords(base_next, ui);
-            const bool gen_next = last_kt ? (rg < nact_next) : active;
-            double* anext = a_tiles + (size_t)((it + 1) & 1) * a_doubles + grow_in_tile * KC_AP + gj0;
+            bool gen_next = active;
+            if (ktl + 1 == klen) {                                    // the next block belongs to the next segment
+                gen_next = false;
+                if (j + 1 < nseg) {
+                    const Seg sn = seg_info(j + 1);
+                    row_coords(sn.base_rg, ui);
+                    gen_next = rg < sn.nact;
+                }
+            }
+            double* anext = a_tiles + (size_t)(par ^ 1) * a_doubles + grow_in_tile * KC_AP + gj0;
             double tv[4] = {0.0, 0.0, 0.0, 0.0};
             if (KIND == KC_KIND_TABLE && gen_next) {
                 // structured grid: the four kernel values are table look-ups (L1/L2 hits, no FP64 pipe
@@ -383,13 +466,13 @@ __global__ void __launch_bounds__(KC_THREADS, 1) kcov_gemm_kernel(const __grid_c
             }
             // ---- tensor-core phase on the current k-tile: wait until the whole row group has
             //      published this block (and has stopped reading the other buffer)
-            mbar_wait(&abar[rg], (uint32_t)(it & 1));
+            mbar_wait(&abar[rg], (uint32_t)par);
             __syncwarp();
             const double* arow0 = as + (rg * 16 + g) * KC_AP + t;
             const double* arow1 = arow0 + 8 * KC_AP;
 #pragma unroll
             for (int ks = 0; ks < KC_BK / 4; ++ks) {
-                // one kernel value of the NEXT k-tile every second k-step: a single exp chain
+                // one kernel value of the NEXT block every second k-step: a single exp chain
                 // is live at a time and its DFMAs interleave with this step's DMMAs
                 if (KIND != KC_KIND_TABLE && (ks & 1) == 0 && gen_next) {
                     const int e = ks >> 1;
@@ -427,29 +510,67 @@ __global__ void __launch_bounds__(KC_THREADS, 1) kcov_gemm_kernel(const __grid_c
             }
         }
 
-        // epilogue: W = sigma2 * acc + nugget * X[global row]
+        const Seg sg = seg_info(j);
+        if (sg.slot < 0) {
+            // epilogue of a full round: W = sigma2 * acc + nugget * X[global row]
 #pragma unroll
-        for (int h = 0; h < 2; ++h) {
-            const int64_t lrow = (base_rg + rg) * 16 + h * 8 + g;
-            if (active && lrow < p.mloc) {
-                double* wrow = p.W + lrow * p.ldw + nb0 * 8 + 2 * t;
-                const double* xg = p.X + (p.row0 + lrow) * p.ld + nb0 * 8 + 2 * t;
+            for (int h = 0; h < 2; ++h) {
+                const int64_t lrow = (sg.base_rg + rg) * 16 + h * 8 + g;
+                if (active && lrow < p.mloc) {
+                    double* wrow = p.W + lrow * p.ldw + nb0 * 8 + 2 * t;
+                    const double* xg = p.X + (p.row0 + lrow) * p.ld + nb0 * 8 + 2 * t;
 #pragma unroll
-                for (int nb = 0; nb < NBW; ++nb) {
-                    if (nb0 + nb < NB) {
-                        double2 v;
-                        v.x = p.sigma2 * acc[h][nb][0];
-                        v.y = p.sigma2 * acc[h][nb][1];
-                        if (p.nugget != 0.0) {
-                            const double2 xv = *reinterpret_cast<const double2*>(xg + nb * 8);
-                            v.x += p.nugget * xv.x;
-                            v.y += p.nugget * xv.y;
+                    for (int nb = 0; nb < NBW; ++nb) {
+                        if (nb0 + nb < NB) {
+                            double2 v;
+                            v.x = p.sigma2 * acc[h][nb][0];
+                            v.y = p.sigma2 * acc[h][nb][1];
+                            if (p.nugget != 0.0) {
+                                const double2 xv = *reinterpret_cast<const double2*>(xg + nb * 8);
+                                v.x += p.nugget * xv.x;
+                                v.y += p.nugget * xv.y;
+                            }
+                            *reinterpret_cast<double2*>(wrow + nb * 8) = v;
                         }
-                        *reinterpret_cast<double2*>(wrow + nb * 8) = v;
                     }
                 }
             }
+        } else if (active) {
+            // tail segment: raw partial sums of this k range -> slot (kcov_tail_fixup_kernel combines them)
+            double* part = p.partial + (size_t)sg.slot * KC_BM * p.ldw;
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                double* prow = part + (size_t)(rg * 16 + h * 8 + g) * p.ldw + nb0 * 8 + 2 * t;
+#pragma unroll
+                for (int nb = 0; nb < NBW; ++nb)
+                    if (nb0 + nb < NB) *reinterpret_cast<double2*>(prow + nb * 8) = make_double2(acc[h][nb][0], acc[h][nb][1]);
+            }
         }
+    }
+}
+
+// Tail tiles: W[rows of tile t] = sigma2 * (sum of the k-range pieces in ascending CTA order) + nugget * X[rows].
+// Piece of CTA b for tile t lives in slot 2b (tile t is the first tile of b's share) or 2b + 1.
+__global__ void kcov_tail_fixup_kernel(KcovParams p, int64_t nkt, int64_t tail_rg0, int grid_main, int cols) {
+    const int64_t tile = blockIdx.x;
+    const int64_t ulo = tile * nkt, uhi = ulo + nkt;                  // this tile's units
+    const int b_first = (int)(ulo / p.tail_u);
+    int b_last = (int)((uhi - 1) / p.tail_u);
+    if (b_last > grid_main - 1) b_last = grid_main - 1;
+    const int64_t row_base = tail_rg0 * 16 + tile * KC_BM;
+    for (int idx = threadIdx.x; idx < KC_BM * cols; idx += blockDim.x) {
+        const int r = idx / cols, c = idx - r * cols;
+        const int64_t lrow = row_base + r;
+        if (lrow >= p.mloc) continue;
+        double s = 0.0;
+        for (int b = b_first; b <= b_last; ++b) {
+            const int64_t first_tile = ((int64_t)b * p.tail_u) / nkt;
+            const int slot = 2 * b + (tile == first_tile ? 0 : 1);
+            s += p.partial[((size_t)slot * KC_BM + r) * p.ldw + c];
+        }
+        double v = p.sigma2 * s;
+        if (p.nugget != 0.0) v += p.nugget * p.X[(p.row0 + lrow) * p.ld + c];
+        p.W[lrow * p.ldw + c] = v;
     }
 }
 
@@ -491,9 +612,27 @@ static void launch_kcov(gsi_ctx* ctx, const KcovParams& p0) {
         GSI_CUDA(cudaMemsetAsync(ctx->sweep_cnt, 0, n_epochs * sizeof(unsigned int), ctx->stream));
         p.sync_cnt = ctx->sweep_cnt;
     }
+    // stream-K tail: tiles left over after the full rounds, cut into equal k shares (one per CTA)
+    const int64_t nkt_h = (p.n + KC_BK - 1) / KC_BK;
+    const int64_t full_rounds_h = total_rg / (grid * 4);
+    const int64_t tail_rg0_h = full_rounds_h * grid * 4;
+    const int64_t tail_tiles_h = (total_rg - tail_rg0_h + 3) / 4;
+    p.tail_u = tail_tiles_h > 0 ? (tail_tiles_h * nkt_h + grid - 1) / grid : 0;
+    p.partial = nullptr;
+    size_t part_bytes = 0;
+    if (tail_tiles_h > 0) {
+        part_bytes = (size_t)2 * grid * KC_BM * p.ldw * sizeof(double);
+        p.partial = static_cast<double*>(pool_alloc(ctx, part_bytes));
+    }
+    struct PartGuard { gsi_ctx* c; void* q; size_t b; ~PartGuard() { if (q) pool_free(c, q, b); } } pguard{ctx, p.partial, part_bytes};
     kfn<<<(unsigned)grid, KC_THREADS, smem, ctx->stream>>>(p);
     GSI_CUDA(cudaGetLastError());
     count_launch(ctx);
+    if (tail_tiles_h > 0) {
+        kcov_tail_fixup_kernel<<<(unsigned)tail_tiles_h, 512, 0, ctx->stream>>>(p, nkt_h, tail_rg0_h, (int)grid, 8 * NB);
+        GSI_CUDA(cudaGetLastError());
+        count_launch(ctx);
+    }
 }
 
 template <int NB, int KIND>
