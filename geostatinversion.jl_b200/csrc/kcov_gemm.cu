@@ -347,7 +347,12 @@ __global__ void __launch_bounds__(KC_THREADS, 1) kcov_gemm_kernel(const __grid_c
     // generation role inside the row group: 128 threads x 4 entries = 16 rows x 32 points
     const int gtid = tid & 127;                  // thread index within the row group
     const int grow_in_tile = rg * 16 + (gtid >> 3);
-    const int gj0 = (gtid & 7) * 4;
+    // my four points of the k-tile: columns gj0, gj0+1 and gj0+16, gj0+17 (gcol(e)).  The eight threads of a row
+    // then publish 16-byte pairs at units 0..7 and 8..15 of the row: conflict-free 128-bit stores (round 1 used
+    // four adjacent columns per thread: units 0,2,..,14 -> every quarter-warp store 2-way conflicted, 56 % of all
+    // shared-store wavefronts of the kernel).
+    const int gj0 = (gtid & 7) * 2;
+    auto gcol = [&](int e) -> int { return gj0 + (e & 1) + ((e >> 1) << 4); };
     int li[DIM];
     auto row_coords = [&](int64_t base_rg, double (&ui)[DIM]) {
         int64_t gpt = p.row0 + base_rg * 16 + grow_in_tile;           // global point of my generated row
@@ -363,7 +368,7 @@ __global__ void __launch_bounds__(KC_THREADS, 1) kcov_gemm_kernel(const __grid_c
         int idx = 0;
 #pragma unroll
         for (int k = DIM - 1; k >= 0; --k) {
-            int dk = li[k] - usi[k * KC_BK + gj0 + e];
+            int dk = li[k] - usi[k * KC_BK + gcol(e)];
             dk = dk < 0 ? -dk : dk;
             idx = (k == DIM - 1) ? dk : idx * (k == 0 ? p.nx : p.ny) + dk;
         }
@@ -375,7 +380,7 @@ __global__ void __launch_bounds__(KC_THREADS, 1) kcov_gemm_kernel(const __grid_c
             double r2 = (KIND == GSI_KERNEL_EXPONENTIAL) ? 1e-300 : 0.0;
 #pragma unroll
             for (int k = 0; k < DIM; ++k) {
-                const double dk = ui[k] - u0[k * ustride + gj0 + e];
+                const double dk = ui[k] - u0[k * ustride + gcol(e)];
                 r2 = fma(dk, dk, r2);
             }
             v[e] = kern_eval<KIND>(r2, p.beta, etab);
@@ -384,7 +389,7 @@ __global__ void __launch_bounds__(KC_THREADS, 1) kcov_gemm_kernel(const __grid_c
     auto store4 = [&](double* as, const double (&v)[4]) {
         double2* dst = reinterpret_cast<double2*>(as + grow_in_tile * KC_AP + gj0);
         dst[0] = make_double2(v[0], v[1]);
-        dst[1] = make_double2(v[2], v[3]);
+        dst[8] = make_double2(v[2], v[3]);          // + 16 columns
     };
 
     int c_s = 0;                       // consumer pipeline stage / mbarrier phase of iteration `it`
@@ -404,7 +409,7 @@ __global__ void __launch_bounds__(KC_THREADS, 1) kcov_gemm_kernel(const __grid_c
                     int idx = 0;
 #pragma unroll
                     for (int k = DIM - 1; k >= 0; --k) {
-                        int dk = li[k] - p.lat[k * p.n_pad + ktf * KC_BK + gj0 + e];
+                        int dk = li[k] - p.lat[k * p.n_pad + ktf * KC_BK + gcol(e)];
                         dk = dk < 0 ? -dk : dk;
                         idx = (k == DIM - 1) ? dk : idx * (k == 0 ? p.nx : p.ny) + dk;
                     }
@@ -479,10 +484,10 @@ __global__ void __launch_bounds__(KC_THREADS, 1) kcov_gemm_kernel(const __grid_c
                     double r2 = (KIND == GSI_KERNEL_EXPONENTIAL) ? 1e-300 : 0.0;
 #pragma unroll
                     for (int k = 0; k < DIM; ++k) {
-                        const double dk = ui[k] - us[k * KC_BK + gj0 + e];
+                        const double dk = ui[k] - us[k * KC_BK + gcol(e)];
                         r2 = fma(dk, dk, r2);
                     }
-                    anext[e] = kern_eval<KIND>(r2, p.beta, etab);
+                    anext[(e & 1) + ((e >> 1) << 4)] = kern_eval<KIND>(r2, p.beta, etab);
                 }
                 if (active) {
                     const double a0 = arow0[ks * 4];
@@ -501,7 +506,7 @@ __global__ void __launch_bounds__(KC_THREADS, 1) kcov_gemm_kernel(const __grid_c
             if (KIND == KC_KIND_TABLE && gen_next) {
                 double2* dst = reinterpret_cast<double2*>(anext);
                 dst[0] = make_double2(tv[0], tv[1]);
-                dst[1] = make_double2(tv[2], tv[3]);
+                dst[8] = make_double2(tv[2], tv[3]);
             }
             __syncwarp();
             if (lane == 0) {

@@ -13,6 +13,9 @@
 //     hardware cluster barrier instead of a kernel boundary, convergence decided on the device.
 //     A round is ~2 L2 round trips of work, so the ~3 us fixed cost of a launch dominated the
 //     per-round version (1881 launches, 10.7 ms at l = 210).  Option "svd.fused".
+//     (Measured alternative, round 2, removed: the matrix held in the cluster's distributed shared
+//     memory instead of L2 -- bit-identical, but SLOWER: 6.5 vs 4.9 ms at l = 210, 5.7 vs 4.4 ms
+//     at the 17 472-point case; remote shared-memory round trips do not beat L2 round trips here.)
 #include "common.cuh"
 #include <cooperative_groups.h>
 

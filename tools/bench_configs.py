@@ -113,4 +113,23 @@ t_app_cpu = best(lambda: S @ V, 2, 1)
 out["c4"] = {"lowrankcov_randsvd_gpu_ms": t_lr_gpu, "lowrankcov_randsvd_cpu_oracle_ms": t_lr_cpu, "parity": c4,
              "sketch_cov_gpu_ms": t_cov, "sketch_cov_cpu_ms": t_cov_cpu,
              "sketch_apply_103cols_gpu_ms_incl_transfers": t_app, "sketch_apply_103cols_cpu_ms": t_app_cpu}
+# ---- a7 / f4: adaptive range finder on a dense 8192^2 matrix of rank 96 (HBM-bound: one pass over A per vector)
+na, ra = 8192, 96
+rng = np.random.default_rng(7)
+Aa = rng.standard_normal((na, ra)) @ rng.standard_normal((ra, na))
+opa = gsi.DenseMatrix(Aa)
+Om0, oms = rng.standard_normal((na, 10)), rng.standard_normal((na, 160))
+Qf = gsi.rangefinder(opa, Omega=Om0, omegas=oms)
+t_f = best(lambda: gsi.rangefinder(opa, Omega=Om0, omegas=oms), 3, 1)
+passes = Qf.shape[1] + 1                      # A * randn(n, r) once, then A * omega per basis vector
+Qb = gsi.rangefinder(opa, omegas=oms, block=32)
+t_b = best(lambda: gsi.rangefinder(opa, omegas=oms, block=32), 3, 1)
+t_o = best(lambda: oracle.rangefinder_adaptive(Aa, Om0, oms), 1, 0)
+out["adaptive"] = {"n": na, "rank": ra,
+                   "faithful_ms": t_f, "faithful_basis": int(Qf.shape[1]), "faithful_passes_over_A": passes,
+                   "faithful_algorithmic_GBps": passes * 8.0 * na * na / (t_f * 1e-3) * 1e-9,
+                   "faithful_residual": float(np.linalg.norm(Aa - Qf @ (Qf.T @ Aa)) / np.linalg.norm(Aa)),
+                   "blocked32_ms": t_b, "blocked32_basis": int(Qb.shape[1]),
+                   "blocked32_residual": float(np.linalg.norm(Aa - Qb @ (Qb.T @ Aa)) / np.linalg.norm(Aa)),
+                   "cpu_oracle_faithful_ms": t_o}
 print(json.dumps(out, indent=1))
