@@ -63,6 +63,7 @@ SIGNATURES = {
     "gsi_buf_zero": (_i32, [_p]),
     "gsi_op_dense": (_i32, [_p, _p, _i64, _i64, _pp]),
     "gsi_op_lowrankcov": (_i32, [_p, _p, _i32, _pp]),
+    "gsi_op_lowrankcov_sharded": (_i32, [_p, _p, _i32, _i64, _i64, _pp]),
     "gsi_op_kernelcov": (_i32, [_p, _i32, _i32, _i64, _pd, _pd, _f64, _f64, _f64, _i64, _i64, _pp]),
     "gsi_op_kernelcov_grid": (_i32, [_p, _i32, _i32, _pi64, _pd, _pd, _f64, _f64, _f64, _i64, _i64, _pp]),
     "gsi_op_free": (_i32, [_p]),

@@ -296,7 +296,9 @@ class LowRankCovMatrix(_Operator):
     mean-removed fields; products run as two tensor-core GEMMs."""
     symmetric = True
 
-    def __init__(self, samples, ctx=None, remove_mean=True):
+    def __init__(self, samples, ctx=None, remove_mean=True, row0=0, n_global=None):
+        """samples: list of fields or n x N matrix.  Multi-rank context: pass this rank's rows
+        samples[row0 : row0 + mloc] and the global field length n_global."""
         super().__init__(ctx or default_context())
         if isinstance(samples, (list, tuple)):
             S = np.stack([np.asarray(s, dtype=np.float64) for s in samples], axis=1)
@@ -305,8 +307,13 @@ class LowRankCovMatrix(_Operator):
         S = _f64_colmajor(S)
         self.nsamples = S.shape[1]
         self._buf = DeviceMatrix.from_host(self.ctx, S, LAYOUT_COLMAJOR)
-        self.row0, self.mloc = 0, S.shape[0]
-        check(self._lib.gsi_op_lowrankcov(self.ctx._h, self._buf._h, 1 if remove_mean else 0, C.byref(self._h)))
+        self.row0, self.mloc = int(row0), S.shape[0]
+        n_global = S.shape[0] if n_global is None else int(n_global)
+        if self.row0 == 0 and n_global == S.shape[0]:
+            check(self._lib.gsi_op_lowrankcov(self.ctx._h, self._buf._h, 1 if remove_mean else 0, C.byref(self._h)))
+        else:
+            check(self._lib.gsi_op_lowrankcov_sharded(self.ctx._h, self._buf._h, 1 if remove_mean else 0, self.row0,
+                                                      n_global, C.byref(self._h)))
 
     @classmethod
     def from_device(cls, samples, remove_mean=True):

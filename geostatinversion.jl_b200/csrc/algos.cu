@@ -15,7 +15,7 @@ BufPtr make_buf(gsi_ctx* ctx, int32_t layout, int64_t rows, int64_t cols) {
     BufPtr b(new gsi_buf());
     b->ctx = ctx; b->layout = layout; b->rows = rows; b->cols = cols;
     if (layout == GSI_LAYOUT_TALL) {
-        GSI_REQUIRE(cols <= kMaxCols, GSI_ERR_UNSUPPORTED, "TALL buffers hold at most 256 columns");
+        GSI_REQUIRE(cols <= kMaxWideCols, GSI_ERR_UNSUPPORTED, "TALL buffers hold at most 1024 columns");
         b->ld = ld_for_cols(cols);
         b->rows_alloc = round_up(rows > 0 ? rows : 1, kRowPad);
     } else if (layout == GSI_LAYOUT_COLMAJOR) {
@@ -98,15 +98,24 @@ void op_apply(gsi_op* op, int trans, const gsi_buf* X, gsi_buf* Y) {
             break;
         }
         case OP_LOWRANKCOV: {
-            // S (S' X) / (N-1)   (reference src/lowrank.jl:115-121 as two skinny GEMMs)
-            GSI_REQUIRE(ctx->world == 1, GSI_ERR_UNSUPPORTED, "lowrankcov operator is single-GPU");
+            // S (S' X) / (N-1)   (reference src/lowrank.jl:115-121 as two skinny GEMMs).  Row-sharded: this rank
+            // holds the rows [row0, row0 + mloc) of S; T = sum over ranks of S_g' X_g is one small (N x l)
+            // all-reduce, the second product is local.
             const int64_t N = op->A->cols;
             if (!op->tmpT || op->tmpT->cols != X->cols) {
                 if (op->tmpT) BufDeleter()(op->tmpT);
                 op->tmpT = make_buf(ctx, GSI_LAYOUT_TALL, N, X->cols).release();
             }
+            gsi_buf xv = *X;
+            xv.owns = false;
+            if (ctx->world > 1) {
+                GSI_REQUIRE(X->rows == op->n, GSI_ERR_DIMENSION_MISMATCH, "lowrankcov: X must hold all n rows");
+                xv.d = X->d + op->row0 * X->ld;
+                xv.rows = op->mloc;
+            }
             timed_begin(ctx);
-            dense_apply(ctx, op->A, 1, X, op->tmpT, 1.0);
+            dense_apply(ctx, op->A, 1, &xv, op->tmpT, 1.0);
+            if (ctx->world > 1) comm_allreduce_sum(ctx, op->tmpT->d, (size_t)op->tmpT->rows_alloc * op->tmpT->ld);
             dense_apply(ctx, op->A, 0, op->tmpT, Y, op->scale);
             timed_end(ctx, 4.0 * (double)op->A->rows * (double)N * (double)X->cols, 2);
             break;

@@ -199,6 +199,10 @@ static void ctx_really_destroy(gsi_ctx* ctx) {
     if (ctx->sweep_cnt) cudaFree(ctx->sweep_cnt);
     if (ctx->jflags) cudaFree(ctx->jflags);
     if (ctx->pxch) cudaFree(ctx->pxch);
+    for (int i = 0; i < 2; ++i) {
+        if (ctx->pin[i]) cudaFreeHost(ctx->pin[i]);
+        if (ctx->pin_ev[i]) cudaEventDestroy(ctx->pin_ev[i]);
+    }
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
     for (cudaEvent_t e : ctx->ev_pool) cudaEventDestroy(e);
@@ -434,26 +438,37 @@ __global__ void remove_mean_kernel(double* __restrict__ S, int64_t ld, int64_t n
     for (int64_t c = 0; c < N; ++c) S[c * ld + i] -= mean;
 }
 
+static void make_lowrankcov(gsi_ctx* ctx, gsi_buf* samples, int32_t remove_mean, int64_t row0, int64_t n_global, gsi_op** out) {
+    use(ctx);
+    GSI_REQUIRE(samples && out, GSI_ERR_INVALID_ARGUMENT, "null argument");
+    GSI_REQUIRE(samples->layout == GSI_LAYOUT_COLMAJOR, GSI_ERR_INVALID_ARGUMENT, "samples must be a COLMAJOR buffer");
+    GSI_REQUIRE(samples->cols >= 2, GSI_ERR_INVALID_ARGUMENT, "LowRankCovMatrix needs at least 2 samples");
+    GSI_REQUIRE(row0 >= 0 && row0 + samples->rows <= n_global, GSI_ERR_INVALID_ARGUMENT, "lowrankcov: bad row block");
+    std::unique_ptr<gsi_op> op(new gsi_op());
+    op->ctx = ctx; op->type = OP_LOWRANKCOV; op->A = samples;
+    op->m = op->n = n_global; op->row0 = row0; op->mloc = samples->rows;
+    op->scale = 1.0 / (double)(samples->cols - 1);
+    if (remove_mean && samples->rows > 0) {        // the mean is over the samples, row by row: local to the row block
+        remove_mean_kernel<<<(unsigned)((samples->rows + 255) / 256), 256, 0, ctx->stream>>>(samples->d, samples->ld,
+                                                                                             samples->rows, samples->cols);
+        GSI_CUDA(cudaGetLastError());
+        count_launch(ctx);
+    }
+    set_partition(op.get());
+    ctx_retain(ctx);
+    *out = op.release();
+}
+
 GSI_API int32_t gsi_op_lowrankcov(gsi_ctx* ctx, gsi_buf* samples, int32_t remove_mean, gsi_op** out) {
     return guarded([&] {
-        use(ctx);
-        GSI_REQUIRE(samples && out, GSI_ERR_INVALID_ARGUMENT, "null argument");
-        GSI_REQUIRE(samples->layout == GSI_LAYOUT_COLMAJOR, GSI_ERR_INVALID_ARGUMENT, "samples must be a COLMAJOR buffer");
-        GSI_REQUIRE(samples->cols >= 2, GSI_ERR_INVALID_ARGUMENT, "LowRankCovMatrix needs at least 2 samples");
-        std::unique_ptr<gsi_op> op(new gsi_op());
-        op->ctx = ctx; op->type = OP_LOWRANKCOV; op->A = samples;
-        op->m = op->n = samples->rows; op->row0 = 0; op->mloc = samples->rows;
-        op->scale = 1.0 / (double)(samples->cols - 1);
-        if (remove_mean) {
-            remove_mean_kernel<<<(unsigned)((samples->rows + 255) / 256), 256, 0, ctx->stream>>>(samples->d, samples->ld,
-                                                                                                 samples->rows, samples->cols);
-            GSI_CUDA(cudaGetLastError());
-            count_launch(ctx);
-        }
-        set_partition(op.get());
-        ctx_retain(ctx);
-        *out = op.release();
+        GSI_REQUIRE(samples != nullptr, GSI_ERR_INVALID_ARGUMENT, "null argument");
+        make_lowrankcov(ctx, samples, remove_mean, 0, samples->rows, out);
     });
+}
+
+GSI_API int32_t gsi_op_lowrankcov_sharded(gsi_ctx* ctx, gsi_buf* samples_local, int32_t remove_mean, int64_t row0,
+                                          int64_t n_global, gsi_op** out) {
+    return guarded([&] { make_lowrankcov(ctx, samples_local, remove_mean, row0, n_global, out); });
 }
 
 GSI_API int32_t gsi_op_kernelcov(gsi_ctx* ctx, int32_t kind, int32_t d, int64_t n, const double* coords,
@@ -613,7 +628,7 @@ GSI_API int32_t gsi_svd_small(gsi_ctx* ctx, double* M_host, int64_t ldm, int64_t
     return guarded([&] {
         use(ctx);
         GSI_REQUIRE(M_host && sigma_host, GSI_ERR_INVALID_ARGUMENT, "null argument");
-        GSI_REQUIRE(l >= 1 && l <= kMaxCols && ldm >= l, GSI_ERR_INVALID_ARGUMENT, "svd_small: bad size");
+        GSI_REQUIRE(l >= 1 && l <= kMaxWideCols && ldm >= l, GSI_ERR_INVALID_ARGUMENT, "svd_small: bad size");
         double* dev = nullptr;
         GSI_CUDA(cudaMalloc(&dev, ((size_t)2 * l * l + l) * sizeof(double)));
         std::unique_ptr<double, void (*)(double*)> guard(dev, [](double* p) { cudaFree(p); });

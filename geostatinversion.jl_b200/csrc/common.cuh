@@ -39,6 +39,7 @@ inline int64_t round_up(int64_t x, int64_t m) { return (x + m - 1) / m * m; }
 
 constexpr int kRowPad = 64;        // tall buffers: allocated rows are a multiple of this
 constexpr int kMaxCols = 256;      // widest tall iterate a single GEMM pass handles
+constexpr int kMaxWideCols = 1024; // widest tall iterate at all: wider than kMaxCols goes through the products in 256-column chunks
 constexpr int kPxchMaxCtas = 256;   // panel kernels: CTAs of one cooperative launch
 constexpr int kPxchRec = 40;        // doubles per published record
 constexpr size_t kPxchDoubles = (size_t)2 * kPxchMaxCtas * kPxchRec;
@@ -47,7 +48,9 @@ constexpr size_t kPxchDoubles = (size_t)2 * kPxchMaxCtas * kPxchRec;
 //   lp = 8 * NB   (NB = number of 8-column DMMA blocks, from the instantiated list)
 //   ld = lp + 4   (pitch = 4 mod 8 doubles -> conflict-free B-fragment LDS.64)
 int nb_for_cols(int64_t cols);      // smallest instantiated NB with 8*NB >= cols
-inline int64_t ld_for_cols(int64_t cols) { return 8 * (int64_t)nb_for_cols(cols) + 4; }
+inline int64_t ld_for_cols(int64_t cols) {
+    return cols <= kMaxCols ? 8 * (int64_t)nb_for_cols(cols) + 4 : 8 * ((cols + 7) / 8) + 4;      // always 4 mod 8 doubles
+}
 
 }  // namespace gsi
 
@@ -101,6 +104,9 @@ struct gsi_ctx {
     // launches per column (the first round's scheme, kept as the independent implementation to test against)
     int lu_panel = 1;
     int qr_panel = 1;
+    // pinned bounce buffers for uploads from pageable host memory (tall_ops.cu)
+    void* pin[2] = {nullptr, nullptr};
+    cudaEvent_t pin_ev[2] = {nullptr, nullptr};
     // exchange area of the panel kernels (used by nothing else): per-CTA records, double-buffered by column parity
     double* pxch = nullptr;              // [kPxchDoubles]
 };
@@ -145,6 +151,8 @@ namespace gsi {
 // ---- tall_ops.cu
 void tall_zero(gsi_ctx*, gsi_buf*);
 void tall_copy(gsi_ctx*, const gsi_buf* src, gsi_buf* dst);
+// dst[r, 0:w) = src[r, 0:w) for windows of TALL buffers (pointer to the first column + row pitch)
+void tall_cols_copy(gsi_ctx*, const double* src, int64_t lds, double* dst, int64_t ldd, int64_t rows, int64_t w);
 void tall_upload(gsi_buf* b, const double* host, int64_t ldh, int64_t row0, int64_t nrows);
 void tall_download(const gsi_buf* b, double* host, int64_t ldh, int64_t row0, int64_t nrows);
 // out[rows x l2] = Q[rows x l] * M   (M: TALL l x l2 buffer)

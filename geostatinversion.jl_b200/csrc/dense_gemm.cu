@@ -10,6 +10,7 @@
 // 16 x (8*NB/4) strip in registers (one warp issues a DMMA only every ~32 cycles, so the SM
 // needs 3-4 warps per scheduler to keep the FP64 tensor pipe busy -- profiles/r01).
 #include "common.cuh"
+#include "algos.h"
 #include "ptx.cuh"
 #include "nb_list.h"
 
@@ -30,6 +31,13 @@ struct DenseParams {
     int64_t ld, ldw;
     double alpha;
     int stages;
+    // split-K (short-and-wide products: few 64-row output tiles, long reduction -- S'X of the LowRankCovMatrix,
+    // the rga sketch S*V, Q'Y): CTA b works on output tile b / ksplit and k-tiles [part * kt_per, ...) with
+    // part = b % ksplit, and stores raw partial sums to partial[part]; dense_splitk_fixup_kernel adds the parts
+    // in ascending order.  ksplit == 1: the ordinary schedule below.
+    int ksplit;
+    int64_t kt_per;
+    double* partial;      // [ksplit][out_rows][ldw]
 };
 
 template <int NB, int TRANS>
@@ -63,20 +71,26 @@ dense_gemm_kernel(const __grid_constant__ CUtensorMap amap, const __grid_constan
     // not pipe-bound), which removes most of the wave-quantisation loss (n = 32768: 512 tiles on 148 SMs ran as 4
     // rounds at 86 % efficiency; ncu of that launch: DMMA pipe 95 % busy, 28.7 TF/s).
     const int64_t total_rg = (p.out_rows + 15) / 16;
-    const int64_t per_round = (int64_t)gridDim.x * 4;
-    const int64_t full_rounds = total_rg / per_round;
+    const bool splitk = p.ksplit > 1;
+    const int64_t nslots = splitk ? gridDim.x / p.ksplit : gridDim.x;        // CTAs (or CTA groups) sharing the rows
+    const int64_t slot = splitk ? blockIdx.x / p.ksplit : blockIdx.x;
+    const int part = splitk ? (int)(blockIdx.x % p.ksplit) : 0;
+    const int64_t per_round = nslots * 4;
+    const int64_t full_rounds = splitk ? 0 : total_rg / per_round;
     const int64_t remaining = total_rg - full_rounds * per_round;
-    const int64_t q_tail = (remaining + gridDim.x - 1) / gridDim.x;          // 0..4
-    const bool has_tail = remaining > 0 && (int64_t)blockIdx.x * q_tail < remaining;
+    const int64_t q_tail = splitk ? 4 : (remaining + nslots - 1) / nslots;   // 0..4 (split-K: whole 64-row tiles)
+    const bool has_tail = remaining > 0 && slot * q_tail < remaining;
     const int64_t my_rounds = full_rounds + (has_tail ? 1 : 0);
     auto round_base = [&](int64_t j, int& nact) -> int64_t {                 // first row group, active row groups
-        if (j < full_rounds) { nact = 4; return (j * gridDim.x + blockIdx.x) * 4; }
-        const int64_t b0 = (int64_t)blockIdx.x * q_tail;
+        if (j < full_rounds) { nact = 4; return (j * nslots + slot) * 4; }
+        const int64_t b0 = slot * q_tail;
         const int64_t left = remaining - b0;
         nact = (int)(left < q_tail ? left : q_tail);
         return full_rounds * per_round + b0;
     };
-    const int64_t nkt = (p.kdim + DG_BK - 1) / DG_BK;
+    const int64_t nkt_all = (p.kdim + DG_BK - 1) / DG_BK;
+    const int64_t kt_lo = splitk ? part * p.kt_per : 0;                      // my k-tiles [kt_lo, kt_lo + nkt)
+    const int64_t nkt = splitk ? ((nkt_all - kt_lo < p.kt_per) ? nkt_all - kt_lo : p.kt_per) : nkt_all;
     constexpr uint32_t stage_bytes = (uint32_t)(stage_doubles * sizeof(double));
 
     const int64_t total_it = my_rounds * nkt;
@@ -94,9 +108,10 @@ dense_gemm_kernel(const __grid_constant__ CUtensorMap amap, const __grid_constan
         double* xs = smem + (size_t)p_s * stage_doubles;
         double* as = xs + DG_BK * ld;
         mbar_expect_tx(&full[p_s], stage_bytes);
-        bulk_g2s(xs, p.X + p_kt * DG_BK * p.ld, DG_BK * ld * 8, &full[p_s]);
-        if (TRANS) tma_load_2d(as, &amap, (int)(p_kt * DG_BK), (int)p_row, &full[p_s]);
-        else       tma_load_2d(as, &amap, (int)p_row, (int)(p_kt * DG_BK), &full[p_s]);
+        const int64_t ktg = kt_lo + p_kt;                                     // global k-tile
+        bulk_g2s(xs, p.X + ktg * DG_BK * p.ld, DG_BK * ld * 8, &full[p_s]);
+        if (TRANS) tma_load_2d(as, &amap, (int)(ktg * DG_BK), (int)p_row, &full[p_s]);
+        else       tma_load_2d(as, &amap, (int)p_row, (int)(ktg * DG_BK), &full[p_s]);
         ++p_it;
         if (++p_kt == nkt) {
             p_kt = 0;
@@ -159,19 +174,32 @@ dense_gemm_kernel(const __grid_constant__ CUtensorMap amap, const __grid_constan
         for (int h = 0; h < 2; ++h) {
             const int64_t row = (base_rg + rg) * 16 + h * 8 + g;
             if (active && row < p.out_rows) {
-                double* wrow = p.W + row * p.ldw + nb0 * 8 + 2 * t;
+                double* wrow = (splitk ? p.partial + (size_t)part * p.out_rows * p.ldw : p.W) + row * p.ldw + nb0 * 8 + 2 * t;
+                const double sc = splitk ? 1.0 : p.alpha;
 #pragma unroll
                 for (int nb = 0; nb < NBW; ++nb) {
                     if (nb0 + nb < NB) {
                         double2 v;
-                        v.x = p.alpha * acc[h][nb][0];
-                        v.y = p.alpha * acc[h][nb][1];
+                        v.x = sc * acc[h][nb][0];
+                        v.y = sc * acc[h][nb][1];
                         *reinterpret_cast<double2*>(wrow + nb * 8) = v;
                     }
                 }
             }
         }
     }
+}
+
+// W = alpha * (partial[0] + partial[1] + ...) over the first `cols` columns (ascending part order: deterministic)
+__global__ void dense_splitk_fixup_kernel(const double* __restrict__ partial, int ksplit, int64_t out_rows, int64_t ldw,
+                                          int cols, double alpha, double* __restrict__ W) {
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t row = idx / cols;
+    const int c = (int)(idx - row * cols);
+    if (row >= out_rows) return;
+    double s = 0.0;
+    for (int q = 0; q < ksplit; ++q) s += partial[((size_t)q * out_rows + row) * ldw + c];
+    W[row * ldw + c] = alpha * s;
 }
 
 typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -222,13 +250,38 @@ static void launch_dense(gsi_ctx* ctx, const gsi_buf* A, DenseParams p) {
     int occ = 0;
     GSI_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kfn, DG_THREADS, smem));
     if (occ < 1) occ = 1;
-    const int64_t ntiles = (p.out_rows + DG_BM - 1) / DG_BM;       // fewer CTAs than SMs only for tiny outputs
-    int64_t grid = (int64_t)ctx->num_sms * occ;
+    const int64_t ntiles = (p.out_rows + DG_BM - 1) / DG_BM;
+    const int64_t nkt = (p.kdim + DG_BK - 1) / DG_BK;
+    const int64_t ncta = (int64_t)ctx->num_sms * occ;
+    int64_t grid = ncta;
     if (grid > ntiles) grid = ntiles;
     if (grid < 1) grid = 1;
+    // split-K when the output has too few tiles to occupy the device and the reduction is long
+    p.ksplit = 1; p.kt_per = nkt; p.partial = nullptr;
+    size_t part_bytes = 0;
+    if (ntiles * 2 <= ncta && nkt >= 32) {
+        int64_t ks = ncta / ntiles;
+        if (ks > nkt / 8) ks = nkt / 8;                     // at least 8 k-tiles per part
+        if (ks > 1) {
+            p.kt_per = (nkt + ks - 1) / ks;
+            ks = (nkt + p.kt_per - 1) / p.kt_per;           // every part owns at least one k-tile
+            p.ksplit = (int)ks;
+            grid = ntiles * ks;
+            part_bytes = (size_t)ks * p.out_rows * p.ldw * sizeof(double);
+            p.partial = static_cast<double*>(pool_alloc(ctx, part_bytes));
+        }
+    }
+    struct PartGuard { gsi_ctx* c; void* q; size_t b; ~PartGuard() { if (q) pool_free(c, q, b); } } pguard{ctx, p.partial, part_bytes};
     kfn<<<(unsigned)grid, DG_THREADS, smem, ctx->stream>>>(map, p);
     GSI_CUDA(cudaGetLastError());
     count_launch(ctx);
+    if (p.ksplit > 1) {
+        const int64_t total = p.out_rows * (8 * NB);
+        dense_splitk_fixup_kernel<<<(unsigned)((total + 255) / 256), 256, 0, ctx->stream>>>(p.partial, p.ksplit, p.out_rows, p.ldw,
+                                                                                           8 * NB, p.alpha, p.W);
+        GSI_CUDA(cudaGetLastError());
+        count_launch(ctx);
+    }
 }
 
 void dense_apply(gsi_ctx* ctx, const gsi_buf* A, int trans, const gsi_buf* X, gsi_buf* W, double alpha) {
@@ -236,7 +289,18 @@ void dense_apply(gsi_ctx* ctx, const gsi_buf* A, int trans, const gsi_buf* X, gs
     GSI_REQUIRE(X->layout == GSI_LAYOUT_TALL && W->layout == GSI_LAYOUT_TALL, GSI_ERR_INVALID_ARGUMENT,
                 "dense apply: X and W must be TALL");
     GSI_REQUIRE(X->cols == W->cols, GSI_ERR_DIMENSION_MISMATCH, "dense apply: X/W column mismatch");
-    GSI_REQUIRE(X->cols <= kMaxCols, GSI_ERR_UNSUPPORTED, "dense apply: more than 256 columns");
+    if (X->cols > kMaxCols) {
+        // wide iterate (K + p > 256): the product runs on 256-column chunks packed into compact buffers
+        for (int64_t c0 = 0; c0 < X->cols; c0 += kMaxCols) {
+            const int64_t w = (X->cols - c0 < kMaxCols) ? X->cols - c0 : kMaxCols;
+            BufPtr xc = make_buf(ctx, GSI_LAYOUT_TALL, X->rows, w);
+            BufPtr wc = make_buf(ctx, GSI_LAYOUT_TALL, W->rows, w);
+            tall_cols_copy(ctx, X->d + c0, X->ld, xc->d, xc->ld, X->rows, w);
+            dense_apply(ctx, A, trans, xc.get(), wc.get(), alpha);
+            tall_cols_copy(ctx, wc->d, wc->ld, W->d + c0, W->ld, W->rows, w);
+        }
+        return;
+    }
     const int nb = nb_for_cols(X->cols);
     GSI_REQUIRE(X->ld == 8 * nb + 4 && W->ld == X->ld, GSI_ERR_INVALID_ARGUMENT, "dense apply: bad pitch");
     DenseParams p;

@@ -21,6 +21,7 @@
 // Persistent grid: one CTA per SM (x occupancy), static schedule: full rounds of 64-row
 // tiles plus one tail round at 16-row-group granularity (see the schedule comment below).
 #include "common.cuh"
+#include "algos.h"
 #include "ptx.cuh"
 #include "nb_list.h"
 
@@ -664,7 +665,18 @@ void kcov_apply(gsi_op* op, const gsi_buf* X, gsi_buf* W) {
     GSI_REQUIRE(X->rows == op->n, GSI_ERR_DIMENSION_MISMATCH, "kernelcov apply: X must have n rows");
     GSI_REQUIRE(W->rows == op->mloc, GSI_ERR_DIMENSION_MISMATCH, "kernelcov apply: W must have mloc rows");
     GSI_REQUIRE(X->cols == W->cols, GSI_ERR_DIMENSION_MISMATCH, "kernelcov apply: X/W column mismatch");
-    GSI_REQUIRE(X->cols <= kMaxCols, GSI_ERR_UNSUPPORTED, "kernelcov apply: more than 256 columns");
+    if (X->cols > kMaxCols) {
+        // wide iterate (K + p > 256): the product runs on 256-column chunks packed into compact buffers
+        for (int64_t c0 = 0; c0 < X->cols; c0 += kMaxCols) {
+            const int64_t w = (X->cols - c0 < kMaxCols) ? X->cols - c0 : kMaxCols;
+            BufPtr xc = make_buf(ctx, GSI_LAYOUT_TALL, X->rows, w);
+            BufPtr wc = make_buf(ctx, GSI_LAYOUT_TALL, W->rows, w);
+            tall_cols_copy(ctx, X->d + c0, X->ld, xc->d, xc->ld, X->rows, w);
+            kcov_apply(op, xc.get(), wc.get());
+            tall_cols_copy(ctx, wc->d, wc->ld, W->d + c0, W->ld, W->rows, w);
+        }
+        return;
+    }
     const int nb = nb_for_cols(X->cols);
     GSI_REQUIRE(X->ld == 8 * nb + 4 && W->ld == X->ld, GSI_ERR_INVALID_ARGUMENT, "kernelcov apply: bad pitch");
     KcovParams p;

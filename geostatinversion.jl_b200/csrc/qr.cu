@@ -617,7 +617,7 @@ void qr_thinQ_inplace(gsi_ctx* ctx, gsi_buf* Y, double* Rdev) {
     const int64_t need = (n + QP_WARPS * 8 - 1) / (QP_WARPS * 8);
     if (grid > need) grid = (int)(need > 0 ? need : 1);
     const int npanels = (l + QB - 1) / QB;
-    const int lpmax = 8 * nb_for_cols(l);
+    const int lpmax = 8 * nb_for_cols(l < kMaxCols ? l : kMaxCols);     // Gram partial tiles cover <= 256 columns at a time
     // scratch: partial[grid*QB] | tw[QB] | scal | taus[l] | T[npanels*QB*QB] | gpart[num_sms*16*lpmax]
     double* partial = ctx->scratch;
     double* tw = partial + (size_t)grid * QB;
@@ -690,18 +690,20 @@ void qr_thinQ_inplace(gsi_ctx* ctx, gsi_buf* Y, double* Rdev) {
         GSI_CUDA(cudaGetLastError());
         count_launch(ctx);
         if (pe < l) {
-            // trailing update: Y2 <- (I - V T' V') Y2
-            const int ncols = l - pe;
-            int wparts = 0, wlp = 0;
-            gram(ctx, Y->d + (int64_t)pe * Y->ld + ps, Y->ld, pe - ps, Y->d + (int64_t)pe * Y->ld + pe, Y->ld, ncols,
-                 rows_below, gpart, wparts, wlp);
-            BufPtr W2 = make_buf(ctx, GSI_LAYOUT_TALL, pe - ps, ncols);
-            qr_wt_kernel<<<(ncols + QB - 1) / QB, QB * QB, 0, st>>>(Y->d, Y->ld, ps, pe, pe, ncols, gpart, wparts, wlp, T, 1,
-                                                           W2->d, W2->ld);
-            GSI_CUDA(cudaGetLastError());
-            count_launch(ctx);
-            tall_window_update(ctx, Y->d + (int64_t)pe * Y->ld + ps, Y->ld, rows_below, pe - ps, W2.get(),
-                               Y->d + (int64_t)pe * Y->ld + pe, Y->ld, -1.0);
+            // trailing update: Y2 <- (I - V T' V') Y2, in chunks of at most 256 trailing columns (wide iterates)
+            for (int c0 = pe; c0 < l; c0 += kMaxCols) {
+                const int ncols = (l - c0 < kMaxCols) ? l - c0 : kMaxCols;
+                int wparts = 0, wlp = 0;
+                gram(ctx, Y->d + (int64_t)pe * Y->ld + ps, Y->ld, pe - ps, Y->d + (int64_t)pe * Y->ld + c0, Y->ld, ncols,
+                     rows_below, gpart, wparts, wlp);
+                BufPtr W2 = make_buf(ctx, GSI_LAYOUT_TALL, pe - ps, ncols);
+                qr_wt_kernel<<<(ncols + QB - 1) / QB, QB * QB, 0, st>>>(Y->d, Y->ld, ps, pe, c0, ncols, gpart, wparts, wlp, T, 1,
+                                                                       W2->d, W2->ld);
+                GSI_CUDA(cudaGetLastError());
+                count_launch(ctx);
+                tall_window_update(ctx, Y->d + (int64_t)pe * Y->ld + ps, Y->ld, rows_below, pe - ps, W2.get(),
+                                   Y->d + (int64_t)pe * Y->ld + c0, Y->ld, -1.0);
+            }
         }
     }
     if (Rdev) {
@@ -718,18 +720,18 @@ void qr_thinQ_inplace(gsi_ctx* ctx, gsi_buf* Y, double* Rdev) {
         const int pe = (ps + QB < l) ? ps + QB : l;
         const double* T = Tall + (size_t)pi * QB * QB;
         const int64_t rows_below = n - pe;
-        if (pe < l) {
-            const int ncols = l - pe;
+        for (int c0 = pe; c0 < l; c0 += kMaxCols) {
+            const int ncols = (l - c0 < kMaxCols) ? l - c0 : kMaxCols;
             int wparts = 0, wlp = 0;
-            gram(ctx, Y->d + (int64_t)pe * Y->ld + ps, Y->ld, pe - ps, Y->d + (int64_t)pe * Y->ld + pe, Y->ld, ncols,
+            gram(ctx, Y->d + (int64_t)pe * Y->ld + ps, Y->ld, pe - ps, Y->d + (int64_t)pe * Y->ld + c0, Y->ld, ncols,
                  rows_below, gpart, wparts, wlp);
             BufPtr W2 = make_buf(ctx, GSI_LAYOUT_TALL, pe - ps, ncols);
-            qr_wt_kernel<<<(ncols + QB - 1) / QB, QB * QB, 0, st>>>(Y->d, Y->ld, ps, pe, pe, ncols, gpart, wparts, wlp, T, 0,
-                                                           W2->d, W2->ld);
+            qr_wt_kernel<<<(ncols + QB - 1) / QB, QB * QB, 0, st>>>(Y->d, Y->ld, ps, pe, c0, ncols, gpart, wparts, wlp, T, 0,
+                                                                   W2->d, W2->ld);
             GSI_CUDA(cudaGetLastError());
             count_launch(ctx);
             tall_window_update(ctx, Y->d + (int64_t)pe * Y->ld + ps, Y->ld, rows_below, pe - ps, W2.get(),
-                               Y->d + (int64_t)pe * Y->ld + pe, Y->ld, -1.0);
+                               Y->d + (int64_t)pe * Y->ld + c0, Y->ld, -1.0);
         }
         const int64_t prow = n - ps;
         org_m_kernel<<<1, QB * QB, 0, st>>>(Y->d, Y->ld, ps, pe, T, Mscr);

@@ -98,9 +98,10 @@ void tall_window_update(gsi_ctx* ctx, const double* Pd, int64_t ldp, int64_t row
     const int ncols = (int)X->cols;
     const int kpad = ((int)kdim + 3) & ~3;
     const size_t smem = (size_t)kpad * X->ld * sizeof(double);
+    GSI_REQUIRE(smem <= 160 * 1024, GSI_ERR_UNSUPPORTED, "window update: rank x width exceeds the shared-memory copy of U");
     static bool attr_set = false;
     if (!attr_set) {
-        GSI_CUDA(cudaFuncSetAttribute(rank_update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 32 * 260 * 8));
+        GSI_CUDA(cudaFuncSetAttribute(rank_update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
         attr_set = true;
     }
     const int64_t units = ((rows + 15) / 16) * ((ncols + 31) / 32);

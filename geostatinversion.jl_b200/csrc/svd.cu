@@ -166,7 +166,7 @@ jacobi_fused_kernel(double* __restrict__ M, int64_t ld, int rows_dot, int rows_a
 // columns to U in sorted order.
 __global__ void jacobi_finalize_kernel(const double* __restrict__ M, int l, double* __restrict__ U,
                                        double* __restrict__ sigma) {
-    __shared__ double s_sig[kMaxCols];
+    __shared__ double s_sig[kMaxWideCols];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
     for (int j = warp; j < l; j += nw) {
         double a = 0.0;
@@ -278,7 +278,7 @@ void jacobi_sweeps(gsi_ctx* ctx, double* M, int64_t ld, int rows_dot, int rows_a
 
 // M: l x l column-major (ld = l), device.  U (l x l, ld = l) and sigma (l) device outputs.
 void svd_small(gsi_ctx* ctx, double* M, int l, double* U, double* sigma, bool defer_check) {
-    GSI_REQUIRE(l >= 1 && l <= kMaxCols, GSI_ERR_UNSUPPORTED, "svd_small: l must be in 1..256");
+    GSI_REQUIRE(l >= 1 && l <= kMaxWideCols, GSI_ERR_UNSUPPORTED, "svd_small: l must be in 1..1024");
     jacobi_sweeps(ctx, M, l, l, l, l, defer_check);
     jacobi_finalize_kernel<<<1, 1024, 0, ctx->stream>>>(M, l, U, sigma);
     GSI_CUDA(cudaGetLastError());

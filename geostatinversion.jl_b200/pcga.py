@@ -201,9 +201,15 @@ class LinearForwardModel:
         return out
 
 
+MAX_XIS = 253      # the paramstorun batch [xis.., X, s, s] is one device iterate of at most 256 columns
+
+
 def _xis_to_device(ctx, xis):
     if isinstance(xis, DeviceMatrix):
         return xis, xis.shape[1], False
+    if len(xis) > MAX_XIS:
+        raise ValueError(f"pcgalsqr / pcgadirect / rga take at most {MAX_XIS} xis on the device path "
+                         f"(the batch of K+3 parameter vectors is one device iterate of <= 256 columns); got {len(xis)}")
     Zk = np.stack([np.asarray(x, dtype=np.float64) for x in xis], axis=1)
     return DeviceMatrix.from_host(ctx, Zk), Zk.shape[1], True
 

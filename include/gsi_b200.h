@@ -55,7 +55,8 @@ extern "C" {
 #define GSI_ERR_NO_CONVERGENCE 10
 
 /* device layouts of a buffer */
-#define GSI_LAYOUT_TALL 0     /* n x l iterate (l <= 256): Omega, Y, Q, Z, eta batches ...     */
+#define GSI_LAYOUT_TALL 0     /* n x l iterate (l <= 1024): Omega, Y, Q, Z, eta batches ...; wider than 256
+                                 columns runs the operator products in 256-column chunks          */
 #define GSI_LAYOUT_COLMAJOR 1 /* dense operator storage (A, samples, sketch S, H)              */
 
 /* covariance kernels of the matrix-free operator (NEW: the reference contains no
@@ -144,6 +145,11 @@ int32_t gsi_op_dense(gsi_ctx* ctx, gsi_buf* A_local, int64_t row0, int64_t m_glo
  * device (the constructor's lines 17-27).  Products are S (S' B) / (N-1)
  * (src/lowrank.jl:115-133).                                                          */
 int32_t gsi_op_lowrankcov(gsi_ctx* ctx, gsi_buf* samples, int32_t remove_mean, gsi_op** out);
+/* The same operator row-sharded over the ranks of a multi-GPU context: samples_local holds the rows
+ * [row0, row0 + rows) of the n_global x N sample matrix (the sample mean is per row, hence local);
+ * a product exchanges one N x l all-reduce.                                          */
+int32_t gsi_op_lowrankcov_sharded(gsi_ctx* ctx, gsi_buf* samples_local, int32_t remove_mean, int64_t row0,
+                                  int64_t n_global, gsi_op** out);
 /* Matrix-free covariance operator (NEW type with LowRankCovMatrix's method set).
  * coords: host, d x n column-major (point j = coords[j*d .. j*d+d)); ell: d length
  * scales.  This rank applies rows [row0, row0+mloc) of C.  d in {1,2,3}.             */

@@ -55,6 +55,17 @@ def main():
         c = oracle.compare_Z(Zd, oracle.randsvd(A, Om, 30, 8, 2), 30)
         results["dense_sharded"] = c
         ok = ok and c["sv_rel"] < 1e-10 and c["sine"] < 1e-8
+    # row-sharded LowRankCovMatrix (one N x l all-reduce per product) vs the oracle's operator
+    fields = [rng.standard_normal(1500) * (1.0 + np.arange(1500) % 7) for _ in range(40)]
+    r0, ml = gsi.partition_rows(1500, ctx.world, ctx.rank)
+    Sall = np.stack(fields, axis=1)
+    lr = gsi.LowRankCovMatrix(Sall[r0:r0 + ml], ctx=ctx, row0=r0, n_global=1500)
+    Oml = rng.standard_normal((1500, 24))
+    Zl = gsi.randsvd(lr, 20, 4, 2, Omega=Oml, full=True)
+    if ctx.rank == 0:
+        c = oracle.compare_Z(Zl, oracle.randsvd(oracle.LowRankCovMatrix(fields), Oml, 20, 4, 2), 20)
+        results["lowrankcov_sharded"] = c
+        ok = ok and c["sv_rel"] < 1e-10 and c["sine"] < 1e-8
     flag = [ok]
     dist.broadcast_object_list(flag, 0)
     if ctx.rank == 0:

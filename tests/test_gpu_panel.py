@@ -23,7 +23,7 @@ def _with_option(ctx, name, value, fn):
 # (n, l): single CTA; several CTAs; odd panel remainders; the widest iterate; more rows per CTA than
 # shared memory holds (overflow rows worked on in place: n > 148 * 1432)
 LU_SHAPES = [(64, 8), (40, 33), (300, 17), (1000, 60), (5000, 110), (20000, 210), (777, 256), (2049, 16),
-             (230000, 40)]
+             (230000, 40), (3000, 300), (1500, 520)]      # the last two: iterates wider than 256 columns
 
 
 @pytest.mark.parametrize("n,l", LU_SHAPES)
@@ -99,7 +99,7 @@ def test_lu_nan_propagates(gsi):
     assert np.array_equal(masks[0], masks[1])
 
 
-QR_SHAPES = [(64, 8), (1000, 60), (20000, 210), (300, 256), (5000, 33), (2049, 16), (230000, 24)]
+QR_SHAPES = [(64, 8), (1000, 60), (20000, 210), (300, 256), (5000, 33), (2049, 16), (230000, 24), (3000, 300), (1500, 520)]
 
 
 @pytest.mark.parametrize("n,l", QR_SHAPES)
@@ -154,3 +154,21 @@ def test_gaussian_kernel_far_apart_points(gsi):
         Y = op @ X
         assert np.all(np.isfinite(Y))
         assert relerr(Y, X) < 1e-14             # C == I to working precision
+
+
+@pytest.mark.parametrize("K,p,q,dense", [(290, 10, 2, False), (290, 10, 1, True), (560, 40, 1, False)])
+def test_randsvd_wider_than_256_columns(gsi, K, p, q, dense):
+    """randsvd(A, K, p, q) has no width limit in the reference (src/RandMatFact.jl:83): iterates with
+    K + p > 256 columns run the products in 256-column chunks and the factorisations on the wide buffer."""
+    grid, ell = (64, 40), [9.0, 6.0]
+    coords = oracle.grid_coords(grid)
+    n = coords.shape[1]
+    C = oracle.kernel_cov_dense(0, coords, ell)
+    Omega = np.random.default_rng(K).standard_normal((n, K + p))
+    op = gsi.DenseMatrix(C) if dense else gsi.KernelCovMatrix("exponential", coords, ell)
+    Z, S = gsi.randsvd(op, K, p, q, Omega=Omega, return_singular_values=True)
+    assert Z.shape == (n, K + p)
+    c = oracle.compare_Z(Z, oracle.randsvd(C, Omega, K, p, q), K)
+    assert c["tail_zero"] and c["sv_rel"] < 1e-10 and c["sine"] < 1e-8, c
+    X = np.random.default_rng(1).standard_normal((n, 300))
+    assert relerr(op @ X, C @ X) < 1e-12                    # the operator itself on a wide host matrix
