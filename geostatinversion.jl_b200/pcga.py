@@ -378,8 +378,12 @@ class _SketchedModel:
         if hasattr(self.f, "apply_batch"):
             return self.sk.apply(self.f.apply_batch(P))
         Ph = P.numpy()
-        V = np.stack([np.asarray(self.f(np.ascontiguousarray(Ph[:, i])), dtype=np.float64)
-                      for i in range(Ph.shape[1])], axis=1)
+        V = None
+        for i in range(Ph.shape[1]):                            # assembled column-major: no transposing copy on upload
+            v = np.asarray(self.f(np.ascontiguousarray(Ph[:, i])), dtype=np.float64)
+            if V is None:
+                V = np.empty((v.shape[0], Ph.shape[1]), order="F")
+            V[:, i] = v
         return self.sk.apply(V)                                 # all K+3 sketches as one GEMM
 
 

@@ -105,7 +105,7 @@ S = rng.standard_normal((Nred, nobs4)) / np.sqrt(nobs4)
 Rd = np.full(nobs4, 1e-8)
 from gsi_b200.pcga import _Sketch  # noqa: E402
 sk = _Sketch(S, ctx)
-V = rng.standard_normal((nobs4, 103))
+V = np.asfortranarray(rng.standard_normal((nobs4, 103)))     # as rga assembles the K+3 forward runs (column-major)
 t_cov = best(lambda: sk.cov(Rd), 3, 1)
 t_app = best(lambda: sk.apply(V), 3, 1)
 t_cov_cpu = best(lambda: (S * Rd[None, :]) @ S.T, 2, 1)
