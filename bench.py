@@ -20,8 +20,9 @@ value   : Omega already resident in HBM, Z left in HBM.
 e2e     : through the public API with HOST buffers -- Omega uploaded from pinned host
           memory and Z downloaded to pinned host memory inside the timed region.
 parity  : BEFORE the timed region, at every N, the reduced workload (17 472-point Gaussian,
-          same K, p, q; dense: n = 4096) is factored row-sharded over the N ranks and compared
-          with the CPU oracle on rank 0 (singular values, subspace sine, exact-zero tail);
+          same K, p, q; dense: n = 4096) is factored row-sharded over the N ranks; rank 0 compares
+          it with the CPU oracle (singular values, subspace sine, exact-zero tail) after the ranks
+          have left the process group, so that no rank spins on a host core meanwhile;
           `sigma_head` are the first singular values of the TIMED workload, so that agreement
           across N is visible in the scaling run.
 """
@@ -281,7 +282,7 @@ def main():
             torch.cuda.synchronize()
 
     # ------------------------------------------------------------------ parity evidence, before timing
-    parity = None
+    parity, parity_job = None, None
     if not args.no_parity:
         pgrid = PARITY_GRID[args.workload]
         pell = ell[:len(pgrid)]
@@ -291,15 +292,7 @@ def main():
         Om = np.random.default_rng(0).standard_normal((pn, pl))
         Zp = gsi.randsvd(opp, pK, p, q, Omega=Om, full=True)          # gathered on every rank
         opp.free()
-        if rank == 0:
-            import oracle                                                # checker
-            Cd = oracle.kernel_cov_dense(KIND_ID[kind], grid_coords(pgrid), pell)
-            c = oracle.compare_Z(Zp, oracle.randsvd(Cd, Om, pK, p, q), pK)
-            parity = {"sv_rel": c["sv_rel"], "sine": c["sine"], "tail_zero": c["tail_zero"], "n_ranks": world,
-                      "workload": f"{'x'.join(map(str, pgrid))} {kind}, n={pn}, K={pK} p={p} q={q}, row-sharded over "
-                                  f"{world} rank(s), vs oracle.randsvd on the dense matrix (same Omega)",
-                      "ok": bool(c["tail_zero"] and c["sv_rel"] < 1e-10 and c["sine"] < 1e-8)}
-            del Cd
+        parity_job = (Zp, Om, pgrid, pell, pn, pK) if rank == 0 else None     # compared with the oracle at the end
         del Zp
         barrier()
 
@@ -468,12 +461,31 @@ def main():
                "config": cfg, "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roof,
                "phase_ms_per_step": {k: v / args.steps for k, v in phases.items()},
                "parity": parity, "sigma_head": sigma_head, "extra": extra}
-        if not args.no_cpu_baseline:
-            out["cpu_baseline"] = cpu_oracle_run(args.workload, 1, 1)
-        print(json.dumps(out))
+    # All collective work is done: the ranks leave the process group NOW, so that nothing spins on a host
+    # core while rank 0 times the CPU baseline (ranks waiting in an NCCL barrier busy-wait, and OpenBLAS's
+    # spinning worker threads then fight them for cores: measured 0.11 / 0.07 TF/s at N = 2 / 8 against
+    # 0.40 at N = 1 on the same kind of box before this ordering).
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()
+    if rank == 0:
+        if world > 1:
+            time.sleep(2.0)               # let the other ranks exit
+        if parity_job is not None:
+            # the reduced workload was factored on the GPUs BEFORE the timed region; its CPU check runs here
+            import oracle                                                # checker
+            Zp, Om, pgrid, pell, pn, pK = parity_job
+            Cd = oracle.kernel_cov_dense(KIND_ID[kind], grid_coords(pgrid), pell)
+            c = oracle.compare_Z(Zp, oracle.randsvd(Cd, Om, pK, p, q), pK)
+            out["parity"] = {"sv_rel": c["sv_rel"], "sine": c["sine"], "tail_zero": c["tail_zero"], "n_ranks": world,
+                             "workload": f"{'x'.join(map(str, pgrid))} {kind}, n={pn}, K={pK} p={p} q={q}, factored row-sharded "
+                                         f"over {world} rank(s) before the timed region, vs oracle.randsvd on the dense "
+                                         f"matrix (same Omega)",
+                             "ok": bool(c["tail_zero"] and c["sv_rel"] < 1e-10 and c["sine"] < 1e-8)}
+            del Cd
+        if not args.no_cpu_baseline:
+            out["cpu_baseline"] = cpu_oracle_run(args.workload, 1, 1)
+        print(json.dumps(out))
 
 
 if __name__ == "__main__":
