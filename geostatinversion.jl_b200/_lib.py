@@ -57,6 +57,8 @@ SIGNATURES = {
     "gsi_buf_dims": (_i32, [_p, _pi64, _pi64]),
     "gsi_buf_upload": (_i32, [_p, _pd, _i64]),
     "gsi_buf_download": (_i32, [_p, _pd, _i64]),
+    "gsi_host_alloc": (_i32, [_p, _i64, _pp]),
+    "gsi_host_free": (_i32, [_p, _p]),
     "gsi_buf_upload_rows": (_i32, [_p, _i64, _i64, _pd, _i64]),
     "gsi_buf_download_rows": (_i32, [_p, _i64, _i64, _pd, _i64]),
     "gsi_buf_copy": (_i32, [_p, _p]),

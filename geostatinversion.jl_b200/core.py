@@ -85,6 +85,18 @@ class Context:
         check(self._lib.gsi_ctx_get_option(self._h, name.encode(), C.byref(v)))
         return v.value
 
+    def pinned_empty(self, shape):
+        """Column-major Float64 array in page-locked host memory (gsi_host_alloc): uploads from it are
+        plain DMA.  The memory is released when the array (and every view of it) is gone."""
+        shape = tuple(int(x) for x in (shape if isinstance(shape, (tuple, list)) else (shape,)))
+        count = int(np.prod(shape)) if shape else 1
+        ptr = C.c_void_p()
+        check(self._lib.gsi_host_alloc(self._h, max(count, 1) * 8, C.byref(ptr)))
+        owner = _PinnedBlock(self, ptr)
+        buf = (C.c_double * max(count, 1)).from_address(ptr.value)
+        buf._gsi_owner = owner                     # the ctypes array keeps the block alive; NumPy keeps the ctypes array
+        return np.frombuffer(buf, dtype=np.float64, count=count).reshape(shape, order="F")
+
     def close(self):
         if getattr(self, "_h", None) and self._h:
             self._lib.gsi_ctx_destroy(self._h)
@@ -95,6 +107,19 @@ class Context:
             self.close()
         except Exception:
             pass
+
+
+class _PinnedBlock:
+    def __init__(self, ctx, ptr):
+        self.ctx, self.ptr = ctx, ptr
+
+    def __del__(self):
+        try:
+            if self.ptr:
+                self.ctx._lib.gsi_host_free(self.ctx._h if self.ctx._h else None, self.ptr)
+        except Exception:
+            pass
+        self.ptr = None
 
 
 _default_ctx = None

@@ -94,9 +94,9 @@ static void set_option_impl(gsi_ctx* ctx, const std::string& n, int64_t value) {
     else if (n == "kcov.l2_hint") ctx->kcov_l2_hint = v;
     else if (n == "kcov.window") ctx->kcov_window = v;
     else if (n == "kcov.epoch_shift") ctx->kcov_epoch_shift = v;
-    else if (n == "svd.fused") ctx->svd_fused = v != 0;
-    else if (n == "lu.panel") ctx->lu_panel = v != 0;
-    else if (n == "qr.panel") ctx->qr_panel = v != 0;
+    else if (n == "svd.fused") ctx->svd_fused = v < 0 ? 0 : (v > 2 ? 2 : (int)v);
+    else if (n == "lu.panel") ctx->lu_panel = v < 0 ? 0 : (v > 2 ? 2 : (int)v);
+    else if (n == "qr.panel") ctx->qr_panel = v < 0 ? 0 : (v > 2 ? 2 : (int)v);
     else throw Error(GSI_ERR_INVALID_ARGUMENT, "unknown option '" + n + "'");
     try {
         validate_kcov_options(ctx);
@@ -176,7 +176,9 @@ GSI_API int32_t gsi_ctx_create(int32_t device, int32_t rank, int32_t world, cons
         GSI_CUDA(cudaMalloc(&ctx->jflags, 64 * sizeof(int)));
         GSI_CUDA(cudaMalloc(&ctx->pxch, kPxchDoubles * sizeof(double)));
         GSI_CUDA(cudaMemset(ctx->pxch, 0, kPxchDoubles * sizeof(double)));
-        if (const char* e = getenv("GSI_SVD_FUSED")) ctx->svd_fused = atoi(e) != 0;
+        GSI_CUDA(cudaMalloc(&ctx->pbar, kPbarBytes));
+        GSI_CUDA(cudaMemset(ctx->pbar, 0, kPbarBytes));
+        if (const char* e = getenv("GSI_SVD_FUSED")) ctx->svd_fused = atoi(e) < 0 ? 0 : (atoi(e) > 2 ? 2 : atoi(e));
         GSI_CUDA(cudaEventCreate(&ctx->ev0));
         GSI_CUDA(cudaEventCreate(&ctx->ev1));
         if (const char* e = getenv("GSI_SWEEP"))      // "groups,div,hint[,window[,epoch_shift]]": see gsi_ctx_set_option
@@ -199,6 +201,7 @@ static void ctx_really_destroy(gsi_ctx* ctx) {
     if (ctx->sweep_cnt) cudaFree(ctx->sweep_cnt);
     if (ctx->jflags) cudaFree(ctx->jflags);
     if (ctx->pxch) cudaFree(ctx->pxch);
+    if (ctx->pbar) cudaFree(ctx->pbar);
     for (int i = 0; i < 2; ++i) {
         if (ctx->pin[i]) cudaFreeHost(ctx->pin[i]);
         if (ctx->pin_ev[i]) cudaEventDestroy(ctx->pin_ev[i]);
@@ -259,6 +262,7 @@ GSI_API int32_t gsi_ctx_get_option(gsi_ctx* ctx, const char* name, int64_t* valu
         else if (n == "kcov.window") *value_out = ctx->kcov_window;
         else if (n == "kcov.epoch_shift") *value_out = ctx->kcov_epoch_shift;
         else if (n == "svd.fused") *value_out = ctx->svd_fused;
+        else if (n == "svd.last_sweeps") *value_out = ctx->svd_last_sweeps;
         else if (n == "lu.panel") *value_out = ctx->lu_panel;
         else if (n == "qr.panel") *value_out = ctx->qr_panel;
         else throw Error(GSI_ERR_INVALID_ARGUMENT, "unknown option '" + n + "'");
@@ -319,6 +323,33 @@ GSI_API int32_t gsi_buf_free(gsi_buf* buf) {
     return guarded([&] {
         cudaSetDevice(buf->ctx->device);
         BufDeleter()(buf);
+    });
+}
+
+// Page-locked host memory (cudaHostAlloc) for host arrays that are uploaded again and again, e.g. the
+// batch of forward runs an rga iteration sketches: a source in such memory is copied by DMA directly
+// instead of through the context's bounce buffers.
+GSI_API int32_t gsi_host_alloc(gsi_ctx* ctx, int64_t bytes, void** out) {
+    return guarded([&] {
+        use(ctx);
+        GSI_REQUIRE(out != nullptr && bytes >= 0, GSI_ERR_INVALID_ARGUMENT, "gsi_host_alloc: bad argument");
+        *out = nullptr;
+        if (bytes == 0) return;
+        void* q = nullptr;
+        const cudaError_t e = cudaHostAlloc(&q, (size_t)bytes, cudaHostAllocDefault);
+        if (e != cudaSuccess) {
+            cudaGetLastError();
+            throw Error(GSI_ERR_CUDA, std::string("gsi_host_alloc: ") + cudaGetErrorString(e));
+        }
+        *out = q;
+    });
+}
+
+GSI_API int32_t gsi_host_free(gsi_ctx* ctx, void* ptr) {
+    if (!ptr) return GSI_OK;
+    return guarded([&] {
+        if (ctx) GSI_CUDA(cudaSetDevice(ctx->device));      // ctx may be NULL (context already destroyed)
+        GSI_CUDA(cudaFreeHost(ptr));
     });
 }
 

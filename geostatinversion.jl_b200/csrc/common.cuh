@@ -43,6 +43,7 @@ constexpr int kMaxWideCols = 1024; // widest tall iterate at all: wider than kMa
 constexpr int kPxchMaxCtas = 256;   // panel kernels: CTAs of one cooperative launch
 constexpr int kPxchRec = 40;        // doubles per published record
 constexpr size_t kPxchDoubles = (size_t)2 * kPxchMaxCtas * kPxchRec;
+constexpr size_t kPbarBytes = (size_t)(1 + 16) * 32 * sizeof(unsigned int);   // barrier counters of the panel kernels (panel_xch.cuh)
 
 // Width bookkeeping of the "tall" layout (row-major, row pitch ld doubles):
 //   lp = 8 * NB   (NB = number of 8-column DMMA blocks, from the instantiated list)
@@ -98,10 +99,12 @@ struct gsi_ctx {
     // small Jacobi SVD: all sweeps in one cluster launch (svd.cu; gsi_ctx_set_option "svd.fused")
     int svd_fused = 1;
     int* jflags = nullptr;               // [60] rotations per sweep, [60] sweeps used
+    int svd_last_sweeps = 0;             // sweeps of the last single-launch Jacobi run whose verdict was read (option "svd.last_sweeps", read-only)
     bool svd_pending = false;            // a single-launch Jacobi run whose convergence flag has not been read yet
     // factorisation drivers (lu.cu / qr.cu; gsi_ctx_set_option "lu.panel" / "qr.panel"): 1 = one cooperative
     // launch per 16-column panel with the panel rows resident in shared memory (default), 0 = one or two
     // launches per column (the first round's scheme, kept as the independent implementation to test against)
+    // (1: a single thread-block cluster for short iterates, the cooperative grid otherwise; 2: always the grid)
     int lu_panel = 1;
     int qr_panel = 1;
     // pinned bounce buffers for uploads from pageable host memory (tall_ops.cu)
@@ -109,6 +112,7 @@ struct gsi_ctx {
     cudaEvent_t pin_ev[2] = {nullptr, nullptr};
     // exchange area of the panel kernels (used by nothing else): per-CTA records, double-buffered by column parity
     double* pxch = nullptr;              // [kPxchDoubles]
+    unsigned int* pbar = nullptr;        // [kPbarBytes]: two-level barrier counters, zeroed before every factorisation
 };
 
 struct gsi_buf {

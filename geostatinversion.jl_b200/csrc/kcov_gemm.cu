@@ -144,7 +144,11 @@ __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
 // prefetch a few k-tiles ahead of every CTA's sweep -- were run on hardware in round 2
 // (profiles/r02/l2_question.md): both bit-identical, the paced fetch 19 % slower, the prefetch
 // within 0.1 % of the default although it turns every shared-memory fill into an L2 hit.  So an
-// L2-served X stream is not slower as such; both variants were removed.)
+// L2-served X stream is not slower as such; both variants were removed.  A third probe, round 2: the tile fetched
+// as 4 / 8 / 32 bulk copies in an order rotated by the CTA index -- the idea being that CTAs sweeping X in step
+// (sweep window) hammer the same L2 lines in the same order -- made every schedule slower (windowed front 563 ->
+// 623 / 652 / 836 ms, default 516 -> 559 ms: the per-copy cost outweighs any spreading; gpurun_out r03_chunks.log);
+// removed as well.)
 template <int NB, int KIND, int DIM>
 __global__ void __launch_bounds__(KC_THREADS, 1) kcov_gemm_kernel(const __grid_constant__ KcovParams p) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -557,23 +561,33 @@ __global__ void __launch_bounds__(KC_THREADS, 1) kcov_gemm_kernel(const __grid_c
 
 // Tail tiles: W[rows of tile t] = sigma2 * (sum of the k-range pieces in ascending CTA order) + nugget * X[rows].
 // Piece of CTA b for tile t lives in slot 2b (tile t is the first tile of b's share) or 2b + 1.
+// Grid: (tail tiles, KC_BM / KF_ROWS row chunks); the slot list of the tile is built once per CTA (the
+// round-2 version divided 64-bit integers per piece and element on 9 CTAs: 141 us for 9 tiles at n = 10 000).
+constexpr int KF_ROWS = 8;
+constexpr int KF_MAX_PIECES = 160;     // pieces of one tile <= CTAs of the main grid (<= SMs, checked at launch)
 __global__ void kcov_tail_fixup_kernel(KcovParams p, int64_t nkt, int64_t tail_rg0, int grid_main, int cols) {
+    __shared__ int s_slot[KF_MAX_PIECES];
     const int64_t tile = blockIdx.x;
     const int64_t ulo = tile * nkt, uhi = ulo + nkt;                  // this tile's units
     const int b_first = (int)(ulo / p.tail_u);
     int b_last = (int)((uhi - 1) / p.tail_u);
     if (b_last > grid_main - 1) b_last = grid_main - 1;
+    const int npieces = b_last - b_first + 1;
+    for (int k = threadIdx.x; k < npieces; k += blockDim.x) {
+        const int b = b_first + k;
+        const int64_t first_tile = ((int64_t)b * p.tail_u) / nkt;
+        s_slot[k] = 2 * b + (tile == first_tile ? 0 : 1);
+    }
+    __syncthreads();
     const int64_t row_base = tail_rg0 * 16 + tile * KC_BM;
-    for (int idx = threadIdx.x; idx < KC_BM * cols; idx += blockDim.x) {
-        const int r = idx / cols, c = idx - r * cols;
+    const int r_lo = blockIdx.y * KF_ROWS;
+    for (int idx = threadIdx.x; idx < KF_ROWS * cols; idx += blockDim.x) {
+        const int r = r_lo + idx / cols, c = idx % cols;
         const int64_t lrow = row_base + r;
         if (lrow >= p.mloc) continue;
+        const double* src = p.partial + (size_t)r * p.ldw + c;
         double s = 0.0;
-        for (int b = b_first; b <= b_last; ++b) {
-            const int64_t first_tile = ((int64_t)b * p.tail_u) / nkt;
-            const int slot = 2 * b + (tile == first_tile ? 0 : 1);
-            s += p.partial[((size_t)slot * KC_BM + r) * p.ldw + c];
-        }
+        for (int k = 0; k < npieces; ++k) s += src[(size_t)s_slot[k] * KC_BM * p.ldw];
         double v = p.sigma2 * s;
         if (p.nugget != 0.0) v += p.nugget * p.X[(p.row0 + lrow) * p.ld + c];
         p.W[lrow * p.ldw + c] = v;
@@ -635,7 +649,9 @@ static void launch_kcov(gsi_ctx* ctx, const KcovParams& p0) {
     GSI_CUDA(cudaGetLastError());
     count_launch(ctx);
     if (tail_tiles_h > 0) {
-        kcov_tail_fixup_kernel<<<(unsigned)tail_tiles_h, 512, 0, ctx->stream>>>(p, nkt_h, tail_rg0_h, (int)grid, 8 * NB);
+        GSI_REQUIRE(grid <= KF_MAX_PIECES, GSI_ERR_UNSUPPORTED, "kernelcov apply: more CTAs than the tail fix-up handles");
+        kcov_tail_fixup_kernel<<<dim3((unsigned)tail_tiles_h, KC_BM / KF_ROWS), 256, 0, ctx->stream>>>(p, nkt_h, tail_rg0_h,
+                                                                                                      (int)grid, 8 * NB);
         GSI_CUDA(cudaGetLastError());
         count_launch(ctx);
     }

@@ -188,15 +188,20 @@ lu_eliminate_kernel(double* __restrict__ Y, int64_t ld, int64_t nloc, int l, int
 }
 
 // ---------------------------------------------------------------------------- panel driver
-// One cooperative launch per panel [ps, pe).  CTA b owns rows [b*R, (b+1)*R) of Y (R a multiple of 8); its rows
+// One launch per panel [ps, pe).  CTA b owns rows [b*R, (b+1)*R) of Y (R a multiple of 8); its rows
 // >= ps are the "active" ones.  The first `cap` owned rows live in shared memory (pitch LP_PITCH),
 // the rest is worked on in place.
 //
-// Exchange (panel_xch.cuh): per column step every CTA publishes ONE record, then the grid barrier:
+// Exchange (panel_xch.cuh): per column step every CTA publishes ONE record, then the barrier:
 //     [ |candidate|, its row index, the candidate row's 16 panel entries, row k's 16 panel entries (owner only) ].
+// CL = 0: cooperative launch of up to one CTA per SM, records in global memory, two-level counter barrier;
+// CL = 1: the launch is a single thread-block cluster, records pushed into every CTA's shared memory,
+//         hardware cluster barrier (short iterates).
 struct LuPanelParams {
     double* Y; int64_t ld; int64_t n; int l; int ps, pe;
-    double* recs;                   // [2][kPxchMaxCtas][kPxchRec]: val, idx, -, -, row[16], krow[16]
+    double* recs;                   // CL = 0: [2][kPxchMaxCtas][kPxchRec]: val, idx, -, -, row[16], krow[16]
+    unsigned int* bar;              // CL = 0: barrier counters (panel_xch.cuh)
+    unsigned int bar_base;          //         barriers of this factorisation before this launch
     int* flags;
     int64_t R;
     int cap;
@@ -209,24 +214,44 @@ __device__ __forceinline__ void lp_warp_best(double& bv, double& bi) {
     }
 }
 
+template <int CL>
 __global__ void __launch_bounds__(LP_THREADS, 1) lu_panel_kernel(const LuPanelParams p) {
-    cg::grid_group grid = cg::this_grid();
     extern __shared__ double sm[];                 // [cap][LP_PITCH]
+    __shared__ double s_xrec[CL ? 2 * kPxchClusterMax * kPxchRec : 1];   // CL = 1: everybody's records, by parity
     __shared__ double s_bv[LP_WARPS], s_bi[LP_WARPS];
     __shared__ double s_prow[LU_PB], s_krow[LU_PB];
     __shared__ double s_win[2];                    // pivot row index
     __shared__ int s_piv[LU_PB];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, sub = lane & 3, rslot = tid >> 2;
-    const int G = (int)gridDim.x, b = (int)blockIdx.x;
+    const int G = (int)gridDim.x, b = (int)blockIdx.x;       // CL = 1: the grid is one cluster, block rank == blockIdx.x
     const int pb = p.pe - p.ps;
     const int64_t r0 = (int64_t)b * p.R;
     const int64_t r1 = (r0 + p.R < p.n) ? r0 + p.R : p.n;
     const int nown = r1 > r0 ? (int)(r1 - r0) : 0;
     const int64_t ld = p.ld;
     double* Ypan = p.Y + p.ps;                      // panel window of the iterate
+    unsigned int nbar = p.bar_base;
     // panel segment of my local row li (global row r0 + li)
     auto rowp = [&](int li) -> double* {
         return li < p.cap ? sm + (size_t)li * LP_PITCH : Ypan + (r0 + li) * ld;
+    };
+    // entry j of the record CTA q published for column parity par
+    auto rec_rd = [&](int par, int q, int j) -> double {
+        if (CL) return s_xrec[(par * kPxchClusterMax + q) * kPxchRec + j];
+        return __ldcg(p.recs + ((size_t)par * kPxchMaxCtas + q) * kPxchRec + j);
+    };
+    auto rec_wr = [&](int par, int j, double v) {
+        if (CL) {
+            cg::cluster_group cluster = cg::this_cluster();
+            double* mine = s_xrec + (par * kPxchClusterMax + b) * kPxchRec + j;
+            for (int d = 0; d < G; ++d) *cluster.map_shared_rank(mine, d) = v;
+        } else {
+            p.recs[((size_t)par * kPxchMaxCtas + b) * kPxchRec + j] = v;
+        }
+    };
+    auto barrier = [&]() {
+        if (CL) cg::this_cluster().sync();
+        else panel_grid_barrier(p.bar, ++nbar, G, b);
     };
     // ---- load my active rows into shared memory
     const int lfirst = (p.ps > r0) ? (int)((p.ps - r0 < nown) ? p.ps - r0 : nown) : 0;   // first active local row
@@ -241,24 +266,36 @@ __global__ void __launch_bounds__(LP_THREADS, 1) lu_panel_kernel(const LuPanelPa
         }
     }
     __syncthreads();
+    if (CL) cg::this_cluster().sync();             // every CTA of the cluster runs before anybody pushes a record into it
 
     // block arg-max of (bv, bi) -> my record of column step c: candidate + its row, and row `col` if I own it
     auto publish = [&](int col, int c, double bv, double bi) {
         const int par = c & 1;
-        double* rec = p.recs + ((size_t)par * kPxchMaxCtas + b) * kPxchRec;
         lp_warp_best(bv, bi);
         if (lane == 0) { s_bv[warp] = bv; s_bi[warp] = bi; }
         __syncthreads();                                   // also: all rows of this CTA are up to date
-        if (warp == 0) {
+        if (CL) {
+            // every warp reduces the warp candidates (identically); warp w pushes the record into CTA w's copy
             bv = lane < LP_WARPS ? s_bv[lane] : -1.0;
             bi = lane < LP_WARPS ? s_bi[lane] : 0.0;
             lp_warp_best(bv, bi);
-            if (lane == 0) { rec[0] = bv; rec[1] = bi; }
-            if (bv >= 0.0 && lane < pb) rec[4 + lane] = rowp((int)((int64_t)bi - r0))[lane];
+            if (warp < G) {
+                double* dst = cg::this_cluster().map_shared_rank(s_xrec + (par * kPxchClusterMax + b) * kPxchRec, warp);
+                if (lane == 0) { dst[0] = bv; dst[1] = bi; }
+                if (bv >= 0.0 && lane < pb) dst[4 + lane] = rowp((int)((int64_t)bi - r0))[lane];
+                if (col >= r0 && col < r1 && lane >= 16 && lane < 16 + pb)
+                    dst[4 + LU_PB + lane - 16] = rowp((int)(col - r0))[lane - 16];
+            }
+        } else if (warp == 0) {
+            bv = lane < LP_WARPS ? s_bv[lane] : -1.0;
+            bi = lane < LP_WARPS ? s_bi[lane] : 0.0;
+            lp_warp_best(bv, bi);
+            if (lane == 0) { rec_wr(par, 0, bv); rec_wr(par, 1, bi); }
+            if (bv >= 0.0 && lane < pb) rec_wr(par, 4 + lane, rowp((int)((int64_t)bi - r0))[lane]);
         } else if (warp == 1) {
-            if (col >= r0 && col < r1 && lane < pb) rec[4 + LU_PB + lane] = rowp((int)(col - r0))[lane];
+            if (col >= r0 && col < r1 && lane < pb) rec_wr(par, 4 + LU_PB + lane, rowp((int)(col - r0))[lane]);
         }
-        grid.sync();                                       // every CTA's record of this column step is visible
+        barrier();                                         // every CTA's record of this column step is visible
     };
 
     // ---- candidates of the first column of the panel
@@ -277,31 +314,61 @@ __global__ void __launch_bounds__(LP_THREADS, 1) lu_panel_kernel(const LuPanelPa
     for (int k = p.ps; k < p.pe; ++k) {
         const int c = k - p.ps;
         const int par = c & 1;
-        // ---- global pivot: every CTA reduces the G candidates the same way
-        if (warp == 0) {
-            const double* recs = p.recs + (size_t)par * kPxchMaxCtas * kPxchRec;
-            double bv = -1.0, bi = 0.0;
-            int bw = 0;
-            for (int q = lane; q < G; q += 32) {
-                const double v = __ldcg(recs + (size_t)q * kPxchRec), i = __ldcg(recs + (size_t)q * kPxchRec + 1);
-                if (v >= 0.0 && cand_better(v, i, bv, bi)) { bv = v; bi = i; bw = q; }
-            }
+        const int owner_k = (int)(k / p.R);
+        // ---- global pivot: the G candidates reduced the same way everywhere (CTA order, first maximum wins).
+        //      CL = 1: every warp does it for itself from the shared-memory records (no block barrier, no staging);
+        //      CL = 0: warp 0 reads the records from L2 and stages the pivot row / row k for the block.
+        int64_t piv;
+        const double* prow;                                 // the pivot row's panel entries
+        const double* krow;                                 // row k's panel entries before the interchange
+        if (CL) {
+            double bv = lane < G ? rec_rd(par, lane, 0) : -1.0;
+            double bi = lane < G ? rec_rd(par, lane, 1) : 0.0;
+            int bw = lane;
+            if (!(bv >= 0.0)) bv = -1.0;                    // (no candidate)
             for (int o = 1; o < 32; o <<= 1) {
                 const double ov = __shfl_xor_sync(0xffffffffu, bv, o), oi = __shfl_xor_sync(0xffffffffu, bi, o);
                 const int ow = __shfl_xor_sync(0xffffffffu, bw, o);
                 if (cand_better(ov, oi, bv, bi)) { bv = ov; bi = oi; bw = ow; }
             }
-            if (bv < 0.0) { bi = (double)k; }            // no row left (cannot happen for n >= l): no interchange
-            const int owner_k = (int)(k / p.R);
-            if (lane < pb) {
-                s_krow[lane] = __ldcg(recs + (size_t)owner_k * kPxchRec + 4 + LU_PB + lane);
-                s_prow[lane] = bv >= 0.0 ? __ldcg(recs + (size_t)bw * kPxchRec + 4 + lane) : s_krow[lane];
+            krow = s_xrec + (par * kPxchClusterMax + owner_k) * kPxchRec + 4 + LU_PB;
+            if (bv < 0.0) { bi = (double)k; prow = krow; }  // no row left (cannot happen for n >= l): no interchange
+            else prow = s_xrec + (par * kPxchClusterMax + bw) * kPxchRec + 4;
+            piv = (int64_t)bi;
+            if (tid == 0) s_piv[c] = (int)bi;
+        } else {
+            if (warp == 0) {
+                double cv[kPxchMaxCtas / 32], ci[kPxchMaxCtas / 32];
+#pragma unroll
+                for (int it = 0; it < kPxchMaxCtas / 32; ++it) {          // all loads in flight before the first compare
+                    const int q = lane + 32 * it;
+                    cv[it] = q < G ? rec_rd(par, q, 0) : -1.0;
+                    ci[it] = q < G ? rec_rd(par, q, 1) : 0.0;
+                }
+                double bv = -1.0, bi = 0.0;
+                int bw = 0;
+#pragma unroll
+                for (int it = 0; it < kPxchMaxCtas / 32; ++it) {
+                    if (cv[it] >= 0.0 && cand_better(cv[it], ci[it], bv, bi)) { bv = cv[it]; bi = ci[it]; bw = lane + 32 * it; }
+                }
+                for (int o = 1; o < 32; o <<= 1) {
+                    const double ov = __shfl_xor_sync(0xffffffffu, bv, o), oi = __shfl_xor_sync(0xffffffffu, bi, o);
+                    const int ow = __shfl_xor_sync(0xffffffffu, bw, o);
+                    if (cand_better(ov, oi, bv, bi)) { bv = ov; bi = oi; bw = ow; }
+                }
+                if (bv < 0.0) { bi = (double)k; }            // no row left (cannot happen for n >= l): no interchange
+                if (lane < pb) {
+                    s_krow[lane] = rec_rd(par, owner_k, 4 + LU_PB + lane);
+                    s_prow[lane] = bv >= 0.0 ? rec_rd(par, bw, 4 + lane) : s_krow[lane];
+                }
+                if (lane == 0) { s_win[0] = bi; s_piv[c] = (int)bi; }
             }
-            if (lane == 0) { s_win[0] = bi; s_piv[c] = (int)bi; }
+            __syncthreads();
+            piv = (int64_t)s_win[0];
+            prow = s_prow;
+            krow = s_krow;
         }
-        __syncthreads();
-        const int64_t piv = (int64_t)s_win[0];
-        const double pivot = s_prow[c];
+        const double pivot = prow[c];
         double rpiv = 0.0;
         if (pivot == 0.0) {
             if (b == 0 && tid == 0) atomicCAS(&p.flags[0], 0, k + 1);   // first zero pivot (1-based)
@@ -309,23 +376,26 @@ __global__ void __launch_bounds__(LP_THREADS, 1) lu_panel_kernel(const LuPanelPa
             rpiv = 1.0 / pivot;
         }
         const bool use_recip = fabs(pivot) >= 2.2250738585072014e-308;       // dgetf2: sfmin
-        // ---- row interchange inside the panel, each row by its owner
+        // ---- row interchange inside the panel.  Row k receives the pivot row (its owner writes it; nobody reads
+        //      row k again in this panel).  Row piv receives old row k: CL = 1 lazily, by the lanes that eliminate
+        //      it below; CL = 0 by its owner here, followed by a block barrier.
         if (piv != k) {
             if (tid < pb) {
-                if (k >= r0 && k < r1) rowp((int)(k - r0))[tid] = s_prow[tid];
-            } else if (tid >= 32 && tid < 32 + pb) {
-                if (piv >= r0 && piv < r1) rowp((int)(piv - r0))[tid - 32] = s_krow[tid - 32];
+                if (k >= r0 && k < r1) rowp((int)(k - r0))[tid] = prow[tid];
+            } else if (!CL && tid >= 32 && tid < 32 + pb) {
+                if (piv >= r0 && piv < r1) rowp((int)(piv - r0))[tid - 32] = krow[tid - 32];
             }
-            __syncthreads();
+            if (!CL) __syncthreads();
         }
         // ---- elimination of my rows below k, candidates for column k+1
         double bv = -1.0, bi = 0.0;
-        int lstart = (k + 1 > r0) ? (int)((k + 1 - r0 < nown) ? k + 1 - r0 : nown) : 0;
-        for (int base = lstart; base < nown; base += LP_THREADS / 4) {      // warp-uniform trip count
-            const int li = base + rslot;
-            const bool valid = li < nown;
-            double* row = valid ? rowp(li) : sm;
-            const double a = valid ? row[c] : 0.0;
+        double pr[4];                                               // the pivot row entries of my four columns
+#pragma unroll
+        for (int cc = 0; cc < 4; ++cc) pr[cc] = (sub + 4 * cc < pb) ? prow[sub + 4 * cc] : 0.0;
+        // row = my local row li; lazy: it is row piv of a CL = 1 step and still holds the pivot row (takes krow's values)
+        auto eliminate_row = [&](double* row, int li, bool valid) {
+            const bool lazy = CL && valid && piv != k && (r0 + li == piv);
+            const double a = valid ? (lazy ? krow[c] : row[c]) : 0.0;
             __syncwarp();                                   // all four lanes of a row have read a before lane 0 replaces it
             if (valid) {
                 double m;
@@ -336,16 +406,27 @@ __global__ void __launch_bounds__(LP_THREADS, 1) lu_panel_kernel(const LuPanelPa
                 for (int cc = 0; cc < 4; ++cc) {
                     const int j = sub + 4 * cc;
                     if (j > c && j < pb) {
-                        const double v = fma(-m, s_prow[j], row[j]);
+                        const double v = fma(-m, pr[cc], lazy ? krow[j] : row[j]);
                         row[j] = v;
                         if (j == c + 1) {
                             const double av = cand_abs(v);
                             const double gi = (double)(r0 + li);
                             if (cand_better(av, gi, bv, bi)) { bv = av; bi = gi; }
                         }
+                    } else if (lazy && j < c) {
+                        row[j] = krow[j];                   // the L part of old row k moves along
                     }
                 }
             }
+        };
+        const int lstart = (k + 1 > r0) ? (int)((k + 1 - r0 < nown) ? k + 1 - r0 : nown) : 0;
+        for (int base = lstart; base < nres; base += LP_THREADS / 4) {      // rows resident in shared memory (warp-uniform trip count)
+            const int li = base + rslot;
+            eliminate_row(sm + (size_t)(li < nres ? li : 0) * LP_PITCH, li, li < nres);
+        }
+        for (int base = (nres > lstart ? nres : lstart); base < nown; base += LP_THREADS / 4) {  // overflow rows, in place
+            const int li = base + rslot;
+            eliminate_row(Ypan + (r0 + (li < nown ? li : 0)) * ld, li, li < nown);
         }
         if (k + 1 < p.pe) publish(k + 1, c + 1, bv, bi);
     }
@@ -375,27 +456,43 @@ __global__ void __launch_bounds__(LP_THREADS, 1) lu_panel_kernel(const LuPanelPa
             }
         }
     }
+    // CL = 1: nobody's shared memory may be released while a peer can still push a record into it --
+    // the last push precedes the last cluster barrier, after which only local state is touched.
 }
 
 // U12 = L11^{-1} A12 for the panel rows [ps, pe): one thread per trailing column.  The rows are
 // updated in place and copied to the small TALL buffer U (pb x (l - pe)) for the GEMM update.
+// L11 is staged in shared memory first: read from Y inside the substitution, every load would have to
+// wait for the preceding store to the same array (12 us per call for 136 multiply-adds).
 __global__ void lu_u12_kernel(double* __restrict__ Y, int64_t ld, int l, int ps, int pe,
                               double* __restrict__ U, int64_t ldu) {
+    __shared__ double s_l11[LU_PB][LU_PB + 1];
+    const int pb = pe - ps;
+    for (int i = threadIdx.x; i < LU_PB * LU_PB; i += blockDim.x) {
+        const int r = i / LU_PB, c = i % LU_PB;
+        s_l11[r][c] = (r < pb && c < r) ? Y[(int64_t)(ps + r) * ld + ps + c] : 0.0;
+    }
+    __syncthreads();
     const int j = pe + blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= l) return;
     double u[LU_PB];
-    const int pb = pe - ps;
+#pragma unroll
+    for (int r = 0; r < LU_PB; ++r) u[r] = (r < pb) ? Y[(int64_t)(ps + r) * ld + j] : 0.0;
 #pragma unroll
     for (int r = 0; r < LU_PB; ++r) {
         if (r < pb) {
-            const double* yr = Y + (int64_t)(ps + r) * ld;
-            double v = yr[j];
+            double v = u[r];
 #pragma unroll
             for (int c = 0; c < LU_PB; ++c)
-                if (c < r) v -= yr[ps + c] * u[c];
+                if (c < r) v -= s_l11[r][c] * u[c];
             u[r] = v;
-            Y[(int64_t)(ps + r) * ld + j] = v;
-            U[(int64_t)r * ldu + (j - pe)] = v;
+        }
+    }
+#pragma unroll
+    for (int r = 0; r < LU_PB; ++r) {
+        if (r < pb) {
+            Y[(int64_t)(ps + r) * ld + j] = u[r];
+            U[(int64_t)r * ldu + (j - pe)] = u[r];
         }
     }
 }
@@ -437,32 +534,63 @@ void lu_L_inplace(gsi_ctx* ctx, gsi_buf* Y) {
     const size_t xlen = 2 + 2 * (size_t)l;
     const size_t smem = 2 * (size_t)l * sizeof(double);
 
-    // panel driver set-up: cooperative grid of co-resident CTAs, one per SM
+    // panel driver set-up.  Short iterates (lu.panel = 1): the launch is ONE thread-block cluster of up to
+    // 16 CTAs; otherwise (or lu.panel = 2) a cooperative grid of co-resident CTAs, at most one per SM.
     LuPanelParams pp;
-    int pgrid = 0;
+    int pgrid = 0, pmode = 0;                 // pmode 1: cluster transport
     size_t psmem = 0;
-    if (ctx->lu_panel) {
-        const int64_t rmin = 256;                                       // below this a CTA's share is not worth a barrier participant
-        int64_t R = round_up((n + ctx->num_sms - 1) / ctx->num_sms, 8);
-        if (R < rmin) R = rmin;
-        pgrid = (int)((n + R - 1) / R);
-        int cap = (int)R;
+    auto panel_setup = [&](int mode) {
+        pgrid = 0; pmode = mode; psmem = 0;
+        const void* kfn = mode ? (const void*)lu_panel_kernel<1> : (const void*)lu_panel_kernel<0>;
         cudaFuncAttributes fa;
-        GSI_CUDA(cudaFuncGetAttributes(&fa, lu_panel_kernel));
+        GSI_CUDA(cudaFuncGetAttributes(&fa, kfn));
         const int cap_max = (int)((232448 - fa.sharedSizeBytes) / (LP_PITCH * sizeof(double)));   // 227 KB per CTA, minus the static part
+        const int64_t rmin = 256;                                       // below this a CTA's share is not worth a barrier participant
+        const int ctas_max = mode ? kPxchClusterMax : ctx->num_sms;
+        int64_t R = round_up((n + ctas_max - 1) / ctas_max, 8);
+        if (R < rmin) R = rmin;
+        if (mode && R > cap_max + 256) return;                          // too long for one cluster: cooperative grid
+        const int g = (int)((n + R - 1) / R);
+        int cap = (int)R;
         if (cap > cap_max) cap = cap_max;
         psmem = (size_t)cap * LP_PITCH * sizeof(double);
-        GSI_CUDA(cudaFuncSetAttribute(lu_panel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psmem));
-        int occ = 0;
-        GSI_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, lu_panel_kernel, LP_THREADS, psmem));
-        if (occ < 1 || pgrid > ctx->num_sms * occ || pgrid > kPxchMaxCtas) pgrid = 0;   // per-column driver instead
-        if (pgrid > 0) {
-            pp.Y = Y->d; pp.ld = Y->ld; pp.n = n; pp.l = l;
-            pp.recs = ctx->pxch;
-            pp.flags = ctx->dflags;
-            pp.R = R; pp.cap = cap;
+        GSI_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psmem));
+        if (mode) {
+            if (g > 8) GSI_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+        } else {
+            int occ = 0;
+            GSI_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, lu_panel_kernel<0>, LP_THREADS, psmem));
+            if (occ < 1 || g > ctx->num_sms * occ || g > kPxchMaxCtas) return;   // per-column driver instead
         }
-    }
+        pgrid = g;
+        pp.Y = Y->d; pp.ld = Y->ld; pp.n = n; pp.l = l;
+        pp.recs = ctx->pxch;
+        pp.bar = ctx->pbar; pp.bar_base = 0;
+        pp.flags = ctx->dflags;
+        pp.R = R; pp.cap = cap;
+    };
+    if (ctx->lu_panel == 1) panel_setup(1);
+    if (ctx->lu_panel && pgrid == 0) panel_setup(0);
+    if (pgrid > 0 && pmode == 0) GSI_CUDA(cudaMemsetAsync(ctx->pbar, 0, kPbarBytes, ctx->stream));
+    auto panel_launch = [&]() -> cudaError_t {
+        void* args[] = {&pp};
+        if (pmode == 0)
+            return cudaLaunchCooperativeKernel((void*)lu_panel_kernel<0>, dim3((unsigned)pgrid), dim3(LP_THREADS), args,
+                                               psmem, ctx->stream);
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3((unsigned)pgrid);
+        cfg.blockDim = dim3(LP_THREADS);
+        cfg.dynamicSmemBytes = psmem;
+        cfg.stream = ctx->stream;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = (unsigned)pgrid;
+        attr[0].val.clusterDim.y = 1;
+        attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        return cudaLaunchKernelExC(&cfg, (const void*)lu_panel_kernel<1>, args);
+    };
     // per-column driver scratch: cand[grid] | xch[xlen]
     Cand* cand = reinterpret_cast<Cand*>(ctx->scratch);
     double* xch = ctx->scratch + 2 * (size_t)grid;
@@ -473,11 +601,21 @@ void lu_L_inplace(gsi_ctx* ctx, gsi_buf* Y) {
         bool done = false;
         if (pgrid > 0) {
             pp.ps = ps; pp.pe = pe;
-            void* args[] = {&pp};
-            const cudaError_t e = cudaLaunchCooperativeKernel((void*)lu_panel_kernel, dim3((unsigned)pgrid),
-                                                              dim3(LP_THREADS), args, psmem, ctx->stream);
-            if (e == cudaSuccess) {
+            cudaError_t e = panel_launch();
+            if (e != cudaSuccess && pmode == 1) {
+                // the cluster could not be scheduled (partitioned device, no GPC with that many free SMs):
+                // cooperative grid from here on
+                cudaGetLastError();
+                panel_setup(0);
+                if (pgrid > 0) {
+                    GSI_CUDA(cudaMemsetAsync(ctx->pbar, 0, kPbarBytes, ctx->stream));
+                    pp.ps = ps; pp.pe = pe;
+                    e = panel_launch();
+                }
+            }
+            if (pgrid > 0 && e == cudaSuccess) {
                 count_launch(ctx);
+                pp.bar_base += (unsigned int)(pe - ps);     // one barrier per column step
                 done = true;
             } else {
                 cudaGetLastError();            // the grid could not be made co-resident (MPS / partitioned device)

@@ -185,32 +185,56 @@ constexpr int QPK_SLICES = QPK_THREADS / QB;      // 32 slices of the cross-CTA 
 
 struct QrPanelParams {
     double* Y; int64_t ld; int64_t n; int ps, pe;
-    double* recs;                   // [2][kPxchMaxCtas][kPxchRec]: part[16], krow[16]
+    double* recs;                   // CL = 0: [2][kPxchMaxCtas][kPxchRec]: part[16], krow[16]
+    unsigned int* bar;              // CL = 0: barrier counters (panel_xch.cuh)
+    unsigned int bar_base;          //         barriers of this factorisation before this launch
     double* taus;
     int64_t R;
     int cap;
 };
 
+// CL = 0: cooperative grid, records in global memory; CL = 1: the launch is one thread-block cluster,
+// records pushed into every CTA's shared memory (panel_xch.cuh).
+template <int CL>
 __global__ void __launch_bounds__(QPK_THREADS, 1) qr_panel_kernel(const QrPanelParams p) {
-    cg::grid_group grid = cg::this_grid();
     extern __shared__ double sm[];                 // [cap][QPK_PITCH]
+    __shared__ double s_xrec[CL ? 2 * kPxchClusterMax * kPxchRec : 1];   // CL = 1: everybody's records, by parity
     __shared__ double s_red[QPK_SLICES][QB];
     __shared__ double s_wpart[QPK_WARPS][QB];
     __shared__ double s_g[QB], s_tw[QB];
     __shared__ double s_scale;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, sub = lane & 3, rslot = tid >> 2;
-    const int G = (int)gridDim.x, b = (int)blockIdx.x;
+    const int G = (int)gridDim.x, b = (int)blockIdx.x;       // CL = 1: the grid is one cluster
     const int pb = p.pe - p.ps;
     const int64_t r0 = (int64_t)b * p.R;
     const int64_t r1 = (r0 + p.R < p.n) ? r0 + p.R : p.n;
     const int nown = r1 > r0 ? (int)(r1 - r0) : 0;
     const int64_t ld = p.ld;
     double* Ypan = p.Y + p.ps;
+    unsigned int nbar = p.bar_base;
     auto rowp = [&](int li) -> double* {
         return li < p.cap ? sm + (size_t)li * QPK_PITCH : Ypan + (r0 + li) * ld;
     };
     auto first_local = [&](int64_t grow) -> int {       // first local row with global index >= grow
         return grow > r0 ? (int)((grow - r0 < nown) ? grow - r0 : nown) : 0;
+    };
+    // entry j of the record CTA q published for column parity par
+    auto rec_rd = [&](int par, int q, int j) -> double {
+        if (CL) return s_xrec[(par * kPxchClusterMax + q) * kPxchRec + j];
+        return __ldcg(p.recs + ((size_t)par * kPxchMaxCtas + q) * kPxchRec + j);
+    };
+    auto rec_wr = [&](int par, int j, double v) {
+        if (CL) {
+            cg::cluster_group cluster = cg::this_cluster();
+            double* mine = s_xrec + (par * kPxchClusterMax + b) * kPxchRec + j;
+            for (int d = 0; d < G; ++d) *cluster.map_shared_rank(mine, d) = v;
+        } else {
+            p.recs[((size_t)par * kPxchMaxCtas + b) * kPxchRec + j] = v;
+        }
+    };
+    auto barrier = [&]() {
+        if (CL) cg::this_cluster().sync();
+        else panel_grid_barrier(p.bar, ++nbar, G, b);
     };
     const int lfirst = first_local(p.ps);
     const int nres = nown < p.cap ? nown : p.cap;
@@ -224,12 +248,12 @@ __global__ void __launch_bounds__(QPK_THREADS, 1) qr_panel_kernel(const QrPanelP
         }
     }
     __syncthreads();
+    if (CL) cg::this_cluster().sync();             // every CTA of the cluster runs before anybody pushes a record into it
 
     // block reduction of the lanes' psum[cc] (panel column sub + 4cc) -> my record of column step c;
     // the owner of row `col` also publishes that row
     auto publish = [&](int col, int c, double (&psum)[4]) {
         const int par = c & 1;
-        double* rec = p.recs + ((size_t)par * kPxchMaxCtas + b) * kPxchRec;
 #pragma unroll
         for (int cc = 0; cc < 4; ++cc) {
             double v = psum[cc];
@@ -237,15 +261,27 @@ __global__ void __launch_bounds__(QPK_THREADS, 1) qr_panel_kernel(const QrPanelP
             if (lane < 4) s_wpart[warp][sub + 4 * cc] = v;
         }
         __syncthreads();                                   // also: all rows of this CTA are up to date
-        if (tid < QB) {
+        if (CL) {
+            // every warp sums the warp partials (same order everywhere); warp w pushes the record into CTA w's copy
+            double s = 0.0;
+            if (lane < QB) {
+#pragma unroll
+                for (int w = 0; w < QPK_WARPS; ++w) s += s_wpart[w][lane];
+            }
+            if (warp < G) {
+                double* dst = cg::this_cluster().map_shared_rank(s_xrec + (par * kPxchClusterMax + b) * kPxchRec, warp);
+                if (lane < QB) dst[lane] = s;
+                else if (lane - QB < pb && col >= r0 && col < r1) dst[lane] = rowp((int)(col - r0))[lane - QB];
+            }
+        } else if (tid < QB) {
             double s = 0.0;
 #pragma unroll
             for (int w = 0; w < QPK_WARPS; ++w) s += s_wpart[w][tid];
-            rec[tid] = s;
+            rec_wr(par, tid, s);
         } else if (tid >= 32 && tid < 32 + pb) {
-            if (col >= r0 && col < r1) rec[QB + tid - 32] = rowp((int)(col - r0))[tid - 32];
+            if (col >= r0 && col < r1) rec_wr(par, QB + tid - 32, rowp((int)(col - r0))[tid - 32]);
         }
-        grid.sync();                                       // every CTA's record of this column step is visible
+        barrier();                                         // every CTA's record of this column step is visible
     };
 
     // ---- dots of the first panel column with the panel columns, rows > ps
@@ -266,65 +302,101 @@ __global__ void __launch_bounds__(QPK_THREADS, 1) qr_panel_kernel(const QrPanelP
     for (int k = p.ps; k < p.pe; ++k) {
         const int c = k - p.ps;
         const int par = c & 1;
-        const double* recs = p.recs + (size_t)par * kPxchMaxCtas * kPxchRec;
-        const double* krow = recs + (size_t)(k / p.R) * kPxchRec + QB;     // published by the owner of row k
-        const double alpha = __ldcg(krow + c);                             // (issued together with the partials)
-        const double ykj_mine = (tid < pb) ? __ldcg(krow + tid) : 0.0;
-        // ---- every CTA reduces the G partials in the same fixed order
-        {
-            const int j = tid % QB, slice = tid / QB;
-            double s = 0.0;
-            for (int q = slice; q < G; q += QPK_SLICES) s += __ldcg(recs + (size_t)q * kPxchRec + j);
-            s_red[slice][j] = s;
-        }
-        __syncthreads();
-        if (tid < QB) {
-            double s = 0.0;
+        const int owner_k = (int)(k / p.R);                                // its record carries row k
+        const bool own_k = (k >= r0 && k < r1);
+        const double alpha = rec_rd(par, owner_k, QB + c);                 // (issued together with the partials)
+        double scale;
+        double twv[4];                                                     // tw[j] = tau * (v' Y[:, j]) of my four columns
+        if (CL) {
+            // ---- every WARP sums the G partials of column `lane` (CTA order) and derives the Householder scalars
+            //      (dlarfg) for itself: no block barrier between the cluster barrier and the update of the rows
+            double gj = 0.0;
 #pragma unroll
-            for (int sl = 0; sl < QPK_SLICES; ++sl) s += s_red[sl][tid];
-            s_g[tid] = s;
-        }
-        __syncthreads();
-        // ---- Householder scalars (dlarfg), redundantly in every CTA; tw[j] = tau * (v' Y[:, j])
-        {
-            const double xnorm2 = s_g[c];
-            double tau = 0.0, scale = 0.0, beta = alpha;
+            for (int q = 0; q < kPxchClusterMax; ++q)
+                if (q < G && lane < QB) gj += rec_rd(par, q, lane);
+            const double ykj = (lane < pb) ? rec_rd(par, owner_k, QB + lane) : 0.0;
+            const double xnorm2 = __shfl_sync(0xffffffffu, gj, c);
+            double tau = 0.0, beta = alpha;
+            scale = 0.0;
             if (xnorm2 > 0.0) {
                 const double nrm = sqrt(alpha * alpha + xnorm2);
                 beta = (alpha >= 0.0) ? -nrm : nrm;
                 tau = (beta - alpha) / beta;
                 scale = 1.0 / (alpha - beta);
             }
-            if (tid == 0) {
-                s_scale = scale;
-                if (b == 0) p.taus[k] = tau;
+            double t = 0.0;
+            if (lane > c && lane < pb) t = tau * (ykj + scale * gj);      // v' * Y[:, j]   (v_k = 1)
+            if (warp == 0 && own_k) {                                      // row k of R; nobody reads it again in this panel
+                if (lane > c && lane < pb) rowp((int)(k - r0))[lane] = ykj - t;
+                else if (lane == c) rowp((int)(k - r0))[c] = beta;
             }
-            const bool own_k = (k >= r0 && k < r1);
-            if (tid < pb) {
-                const int j = tid;
-                double t = 0.0;
-                if (j > c) {
-                    const double ykj = ykj_mine;
-                    const double w = ykj + scale * s_g[j];         // v' * Y[:, j]   (v_k = 1)
-                    t = tau * w;
-                    if (own_k) rowp((int)(k - r0))[j] = ykj - t;
-                } else if (j == c && own_k) {
-                    rowp((int)(k - r0))[c] = beta;
+            if (tid == 0 && b == 0) p.taus[k] = tau;
+#pragma unroll
+            for (int cc = 0; cc < 4; ++cc) twv[cc] = __shfl_sync(0xffffffffu, t, sub + 4 * cc);
+        } else {
+            const double ykj_mine = (tid < pb) ? rec_rd(par, owner_k, QB + tid) : 0.0;
+            // ---- every CTA reduces the G partials in the same fixed order (all loads in flight before the first add)
+            {
+                const int j = tid % QB, slice = tid / QB;
+                double pv[kPxchMaxCtas / QPK_SLICES];
+#pragma unroll
+                for (int it = 0; it < kPxchMaxCtas / QPK_SLICES; ++it) {
+                    const int q = slice + it * QPK_SLICES;
+                    pv[it] = q < G ? rec_rd(par, q, j) : 0.0;
                 }
-                s_tw[j] = t;
+                double s = 0.0;
+#pragma unroll
+                for (int it = 0; it < kPxchMaxCtas / QPK_SLICES; ++it)
+                    if (slice + it * QPK_SLICES < G) s += pv[it];
+                s_red[slice][j] = s;
             }
+            __syncthreads();
+            if (tid < QB) {
+                double s = 0.0;
+#pragma unroll
+                for (int sl = 0; sl < QPK_SLICES; ++sl) s += s_red[sl][tid];
+                s_g[tid] = s;
+            }
+            __syncthreads();
+            // ---- Householder scalars (dlarfg), redundantly in every CTA; tw[j] = tau * (v' Y[:, j])
+            {
+                const double xnorm2 = s_g[c];
+                double tau = 0.0, sc = 0.0, beta = alpha;
+                if (xnorm2 > 0.0) {
+                    const double nrm = sqrt(alpha * alpha + xnorm2);
+                    beta = (alpha >= 0.0) ? -nrm : nrm;
+                    tau = (beta - alpha) / beta;
+                    sc = 1.0 / (alpha - beta);
+                }
+                if (tid == 0) {
+                    s_scale = sc;
+                    if (b == 0) p.taus[k] = tau;
+                }
+                if (tid < pb) {
+                    const int j = tid;
+                    double t = 0.0;
+                    if (j > c) {
+                        const double ykj = ykj_mine;
+                        const double w = ykj + sc * s_g[j];            // v' * Y[:, j]   (v_k = 1)
+                        t = tau * w;
+                        if (own_k) rowp((int)(k - r0))[j] = ykj - t;
+                    } else if (j == c && own_k) {
+                        rowp((int)(k - r0))[c] = beta;
+                    }
+                    s_tw[j] = t;
+                }
+            }
+            __syncthreads();
+            scale = s_scale;
+#pragma unroll
+            for (int cc = 0; cc < 4; ++cc) twv[cc] = (sub + 4 * cc < pb) ? s_tw[sub + 4 * cc] : 0.0;
         }
-        __syncthreads();
         // ---- rows i > k: v_i = scale * Y[i,k]; Y[i,j] -= v_i * tw[j]; dots of column k+1 (rows > k+1)
-        const double scale = s_scale;
         double psum[4] = {0.0, 0.0, 0.0, 0.0};
         const int lstart = first_local((int64_t)k + 1);
         const int slot = c + 1;                              // panel slot of the next column
-        for (int base = lstart; base < nown; base += QPK_THREADS / 4) {      // warp-uniform trip count
-            const int li = base + rslot;
-            const bool valid = li < nown;
+        auto update_row = [&](double* row, int li, bool valid) {
             double nv[4] = {0.0, 0.0, 0.0, 0.0};
-            double* row = valid ? rowp(li) : sm;
             const double a = valid ? row[c] : 0.0;
             __syncwarp();                                   // all four lanes of a row have read a before it is replaced
             if (valid) {
@@ -333,7 +405,7 @@ __global__ void __launch_bounds__(QPK_THREADS, 1) qr_panel_kernel(const QrPanelP
                 for (int cc = 0; cc < 4; ++cc) {
                     const int j = sub + 4 * cc;
                     if (j >= c && j < pb) {
-                        nv[cc] = (j == c) ? v : row[j] - v * s_tw[j];
+                        nv[cc] = (j == c) ? v : row[j] - v * twv[cc];
                         row[j] = nv[cc];
                     }
                 }
@@ -347,6 +419,14 @@ __global__ void __launch_bounds__(QPK_THREADS, 1) qr_panel_kernel(const QrPanelP
 #pragma unroll
                 for (int cc = 0; cc < 4; ++cc) psum[cc] = fma(ynext, nv[cc], psum[cc]);
             }
+        };
+        for (int base = lstart; base < nres; base += QPK_THREADS / 4) {      // rows resident in shared memory (warp-uniform trip count)
+            const int li = base + rslot;
+            update_row(sm + (size_t)(li < nres ? li : 0) * QPK_PITCH, li, li < nres);
+        }
+        for (int base = (nres > lstart ? nres : lstart); base < nown; base += QPK_THREADS / 4) {   // overflow rows, in place
+            const int li = base + rslot;
+            update_row(Ypan + (r0 + (li < nown ? li : 0)) * ld, li, li < nown);
         }
         if (k + 1 < p.pe) publish(k + 1, c + 1, psum);
     }
@@ -480,25 +560,31 @@ __global__ void qr_tbuild_kernel(const double* __restrict__ Y, int64_t ld, int p
     const int a = threadIdx.x / QB, c = threadIdx.x % QB;     // 256 threads
     double s = 0.0;
     if (a < pb && c < pb && a < c) {
-        for (int b = 0; b < nparts; ++b) s += gpart[(size_t)b * 16 * glp + a * glp + c];
+        const double* gp = gpart + (size_t)a * glp + c;
+#pragma unroll 8
+        for (int b = 0; b < nparts; ++b) s += gp[(size_t)b * 16 * glp];
         for (int r = c; r < pb; ++r) s += vtop(Y, ld, ps, r, a) * vtop(Y, ld, ps, r, c);
     }
     G[a][c] = s;
     Ts[a][c] = 0.0;
     __syncthreads();
-    if (threadIdx.x == 0) {
-        for (int cc = 0; cc < pb; ++cc) {
+    // dlarft recurrence, column by column; the rows of a column are independent (thread r: same
+    // summation order as a serial walk)
+    for (int cc = 0; cc < pb; ++cc) {
+        const int r = threadIdx.x;
+        if (r <= cc) {
             const double tau = taus[ps + cc];
             // T[0:cc, cc] = -tau * T[0:cc, 0:cc] * G[0:cc, cc]
-            for (int r = 0; r < cc; ++r) {
+            if (r < cc) {
                 double z = 0.0;
                 for (int m = r; m < cc; ++m) z += Ts[r][m] * G[m][cc];
                 Ts[r][cc] = -tau * z;
+            } else {
+                Ts[cc][cc] = tau;
             }
-            Ts[cc][cc] = tau;
         }
+        __syncthreads();
     }
-    __syncthreads();
     T[c * QB + a] = Ts[a][c];
 }
 
@@ -629,31 +715,62 @@ void qr_thinQ_inplace(gsi_ctx* ctx, gsi_buf* Y, double* Rdev) {
     const size_t need_doubles = (size_t)(gpart - ctx->scratch) + (size_t)ctx->num_sms * 16 * lpmax;
     GSI_REQUIRE(need_doubles <= ctx->scratch_doubles, GSI_ERR_UNSUPPORTED, "qr: scratch too small");
 
-    // panel driver set-up: cooperative grid of co-resident CTAs, at most one per SM
+    // panel driver set-up.  Short iterates (qr.panel = 1): the launch is ONE thread-block cluster of up to
+    // 16 CTAs; otherwise (or qr.panel = 2) a cooperative grid of co-resident CTAs, at most one per SM.
     QrPanelParams pp;
-    int pgrid = 0;
+    int pgrid = 0, pmode = 0;                 // pmode 1: cluster transport
     size_t psmem = 0;
-    if (ctx->qr_panel) {
-        int64_t R = round_up((n + ctx->num_sms - 1) / ctx->num_sms, 8);
-        if (R < 256) R = 256;
-        pgrid = (int)((n + R - 1) / R);
-        int cap = (int)R;
+    auto panel_setup = [&](int mode) {
+        pgrid = 0; pmode = mode; psmem = 0;
+        const void* kfn = mode ? (const void*)qr_panel_kernel<1> : (const void*)qr_panel_kernel<0>;
         cudaFuncAttributes fa;
-        GSI_CUDA(cudaFuncGetAttributes(&fa, qr_panel_kernel));
+        GSI_CUDA(cudaFuncGetAttributes(&fa, kfn));
         const int cap_max = (int)((232448 - fa.sharedSizeBytes) / (QPK_PITCH * sizeof(double)));   // 227 KB per CTA, minus the static part
+        const int ctas_max = mode ? kPxchClusterMax : ctx->num_sms;
+        int64_t R = round_up((n + ctas_max - 1) / ctas_max, 8);
+        if (R < 256) R = 256;
+        if (mode && R > cap_max + 256) return;                          // too long for one cluster: cooperative grid
+        const int g = (int)((n + R - 1) / R);
+        int cap = (int)R;
         if (cap > cap_max) cap = cap_max;
         psmem = (size_t)cap * QPK_PITCH * sizeof(double);
-        GSI_CUDA(cudaFuncSetAttribute(qr_panel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psmem));
-        int occ = 0;
-        GSI_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, qr_panel_kernel, QPK_THREADS, psmem));
-        if (occ < 1 || pgrid > ctx->num_sms * occ || pgrid > kPxchMaxCtas) pgrid = 0;
-        if (pgrid > 0) {
-            pp.Y = Y->d; pp.ld = Y->ld; pp.n = n;
-            pp.recs = ctx->pxch;
-            pp.taus = taus;
-            pp.R = R; pp.cap = cap;
+        GSI_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psmem));
+        if (mode) {
+            if (g > 8) GSI_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+        } else {
+            int occ = 0;
+            GSI_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, qr_panel_kernel<0>, QPK_THREADS, psmem));
+            if (occ < 1 || g > ctx->num_sms * occ || g > kPxchMaxCtas) return;   // per-column driver instead
         }
-    }
+        pgrid = g;
+        pp.Y = Y->d; pp.ld = Y->ld; pp.n = n;
+        pp.recs = ctx->pxch;
+        pp.bar = ctx->pbar; pp.bar_base = 0;
+        pp.taus = taus;
+        pp.R = R; pp.cap = cap;
+    };
+    if (ctx->qr_panel == 1) panel_setup(1);
+    if (ctx->qr_panel && pgrid == 0) panel_setup(0);
+    if (pgrid > 0 && pmode == 0) GSI_CUDA(cudaMemsetAsync(ctx->pbar, 0, kPbarBytes, st));
+    auto panel_launch = [&]() -> cudaError_t {
+        void* args[] = {&pp};
+        if (pmode == 0)
+            return cudaLaunchCooperativeKernel((void*)qr_panel_kernel<0>, dim3((unsigned)pgrid), dim3(QPK_THREADS), args,
+                                               psmem, st);
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3((unsigned)pgrid);
+        cfg.blockDim = dim3(QPK_THREADS);
+        cfg.dynamicSmemBytes = psmem;
+        cfg.stream = st;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = (unsigned)pgrid;
+        attr[0].val.clusterDim.y = 1;
+        attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        return cudaLaunchKernelExC(&cfg, (const void*)qr_panel_kernel<1>, args);
+    };
     // ---------------- factorisation, panel by panel
     for (int ps = 0, pi = 0; ps < l; ps += QB, ++pi) {
         const int pe = (ps + QB < l) ? ps + QB : l;
@@ -661,11 +778,19 @@ void qr_thinQ_inplace(gsi_ctx* ctx, gsi_buf* Y, double* Rdev) {
         bool done = false;
         if (pgrid > 0) {
             pp.ps = ps; pp.pe = pe;
-            void* args[] = {&pp};
-            const cudaError_t e = cudaLaunchCooperativeKernel((void*)qr_panel_kernel, dim3((unsigned)pgrid),
-                                                              dim3(QPK_THREADS), args, psmem, st);
-            if (e == cudaSuccess) {
+            cudaError_t e = panel_launch();
+            if (e != cudaSuccess && pmode == 1) {
+                cudaGetLastError();            // the cluster could not be scheduled: cooperative grid from here on
+                panel_setup(0);
+                if (pgrid > 0) {
+                    GSI_CUDA(cudaMemsetAsync(ctx->pbar, 0, kPbarBytes, st));
+                    pp.ps = ps; pp.pe = pe;
+                    e = panel_launch();
+                }
+            }
+            if (pgrid > 0 && e == cudaSuccess) {
                 count_launch(ctx);
+                pp.bar_base += (unsigned int)(pe - ps);     // one barrier per column step
                 done = true;
             } else {
                 cudaGetLastError();            // the grid could not be made co-resident: per-column driver

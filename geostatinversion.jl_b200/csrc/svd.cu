@@ -12,7 +12,8 @@
 //     8 CTAs x 32 warps = 256 column pairs, i.e. <= 512 columns), rounds separated by the
 //     hardware cluster barrier instead of a kernel boundary, convergence decided on the device.
 //     A round is ~2 L2 round trips of work, so the ~3 us fixed cost of a launch dominated the
-//     per-round version (1881 launches, 10.7 ms at l = 210).  Option "svd.fused".
+//     per-round version (1881 launches, 10.7 ms at l = 210).  Option "svd.fused" = 2 (and the
+//     fall-back of the block driver below, "svd.fused" = 1).
 //     (Measured alternative, round 2, removed: the matrix held in the cluster's distributed shared
 //     memory instead of L2 -- bit-identical, but SLOWER: 6.5 vs 4.9 ms at l = 210, 5.7 vs 4.4 ms
 //     at the 17 472-point case; remote shared-memory round trips do not beat L2 round trips here.)
@@ -43,13 +44,47 @@ __device__ __forceinline__ int rr_player(int i, int r, int np) {
 __device__ __forceinline__ void jacobi_acc(double x, double y, double& a, double& b, double& g) {
     a = fma(x, x, a); b = fma(y, y, b); g = fma(x, y, g);
 }
+// 1/x for 1e-280 < |x| < 1e280 and 1/sqrt(x) for 1 <= x < 1e300: hardware seed (MUFU, ~2^-20) + two Newton
+// steps, <= 2 ulp.  The scalar chain of a rotation (two divisions, three square roots with the library
+// routines: ~1000 cycles) is the critical path of a Jacobi round -- every warp of a round waits for it --
+// and the rotation only needs c^2 + s^2 = 1 to rounding, not correctly rounded quotients.
+__device__ __forceinline__ double jf_rcp(double x) {
+    double y;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    double e = fma(-x, y, 1.0);
+    y = fma(y, e, y);
+    e = fma(-x, y, 1.0);
+    y = fma(y, e, y);
+    return y;
+}
+__device__ __forceinline__ double jf_rsqrt(double x) {
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    const double h = 0.5 * x;
+    double e = fma(__dmul_rn(-h, y), y, 0.5);
+    y = fma(y, e, y);
+    e = fma(__dmul_rn(-h, y), y, 0.5);
+    y = fma(y, e, y);
+    return y;
+}
 __device__ __forceinline__ bool jacobi_angle(double a, double b, double g, double tol, double& c, double& s) {
-    if (fabs(g) <= tol * sqrt(__dmul_rn(a, b)) || g == 0.0) return false;
-    const double zeta = (b - a) / (2.0 * g);
-    const double tt = (zeta >= 0.0 ? 1.0 : -1.0) / (fabs(zeta) + sqrt(fma(zeta, zeta, 1.0)));
-    c = 1.0 / sqrt(fma(tt, tt, 1.0));
+    const double thr = tol * sqrt(__dmul_rn(a, b));           // independent of the chain below
+    const double ag = fabs(g);
+    double zeta;                                              // (b - a) / (2 g)
+    if (ag > 1e-280 && ag < 1e280) zeta = __dmul_rn(0.5 * (b - a), jf_rcp(g));
+    else zeta = (b - a) / (2.0 * g);
+    const double az = fabs(zeta);
+    double tt;                                                // tan of the rotation angle: sign(zeta) / (|zeta| + sqrt(1 + zeta^2))
+    if (az < 1e150) {
+        const double w = fma(az, az, 1.0);
+        tt = jf_rcp(az + __dmul_rn(w, jf_rsqrt(w)));
+    } else {
+        tt = 0.5 / az;
+    }
+    if (zeta < 0.0) tt = -tt;
+    c = jf_rsqrt(fma(tt, tt, 1.0));
     s = __dmul_rn(c, tt);
-    return true;
+    return !(ag <= thr || g == 0.0);
 }
 __device__ __forceinline__ void jacobi_rot(double c, double s, double x, double y, double& nx, double& ny) {
     nx = fma(c, x, -__dmul_rn(s, y));
@@ -162,6 +197,154 @@ jacobi_fused_kernel(double* __restrict__ M, int64_t ld, int rows_dot, int rows_a
     if (t == 0 && lane == 0) *sweeps_out = done;
 }
 
+// Block one-sided Jacobi, all sweeps in ONE launch of a single cluster of C CTAs (option "svd.fused" = 1,
+// the default where it fits).  The columns form 2C blocks of bs columns.  A sweep is
+//   (a) CTA c orthogonalises the pairs INSIDE blocks 2c and 2c+1 (round-robin inside each block), then
+//   (b) 2C-1 block rounds (round-robin over the blocks): CTA c loads its two blocks (I, J) into SHARED
+//       MEMORY, rotates the bs x bs cross pairs (bs inner rounds of bs disjoint pairs, one warp per
+//       pair, __syncthreads between inner rounds) and writes the blocks back,
+// i.e. every column pair exactly once per sweep (a cyclic ordering, like the flat drivers above) but
+// with ONE cluster barrier per bs inner rounds instead of one per round, and the column data served
+// from shared memory instead of L2: l = 210 runs ~16 barriers + 16 block loads per sweep instead of 209
+// barriers with two L2 round trips each.  The rotation arithmetic is that of the flat drivers; the
+// ordering differs, so results agree with them to rounding, not bit for bit.
+constexpr int JB_MAX_BS = 32;        // columns per block: one warp per cross pair of an inner round
+
+// round-robin player without an integer division (0 <= i < np, 0 <= r < np - 1)
+__device__ __forceinline__ int rr_player_fast(int i, int r, int np) {
+    if (i == 0) return 0;
+    int x = i - 1 + r;
+    if (x >= np - 1) x -= np - 1;
+    return x + 1;
+}
+
+// One column pair of the shared tile (pitch-rpad columns mp, mq; mp is the lower global index).  NR > 0:
+// rpad = 32 * NR, rows >= rows_all are zero, and the two columns stay in registers between the dot
+// products and the rotation (straight-line code: a single warp's dependent instruction stream is what
+// an inner round costs -- the generic-loop version issued ~440 instructions per pair, 3600 cycles).
+template <int NR>
+__device__ __forceinline__ int jb_rotate_pair(double* __restrict__ mp, double* __restrict__ mq, int rows_dot, int rows_all,
+                                              double tol, int lane) {
+    double aa = 0.0, bb = 0.0, gg = 0.0, cs, sn;
+    if (NR > 0) {
+        double x[NR > 0 ? NR : 1], y[NR > 0 ? NR : 1];
+#pragma unroll
+        for (int k = 0; k < NR; ++k) { x[k] = mp[lane + 32 * k]; y[k] = mq[lane + 32 * k]; }
+#pragma unroll
+        for (int k = 0; k < NR; ++k)
+            if (lane + 32 * k < rows_dot) jacobi_acc(x[k], y[k], aa, bb, gg);
+        aa = warp_sum(aa); bb = warp_sum(bb); gg = warp_sum(gg);
+        if (!jacobi_angle(aa, bb, gg, tol, cs, sn)) return 0;
+#pragma unroll
+        for (int k = 0; k < NR; ++k) {
+            double nx, ny;
+            jacobi_rot(cs, sn, x[k], y[k], nx, ny);
+            mp[lane + 32 * k] = nx;
+            mq[lane + 32 * k] = ny;
+        }
+        return 1;
+    }
+    for (int i = lane; i < rows_dot; i += 32) jacobi_acc(mp[i], mq[i], aa, bb, gg);
+    aa = warp_sum(aa); bb = warp_sum(bb); gg = warp_sum(gg);
+    if (!jacobi_angle(aa, bb, gg, tol, cs, sn)) return 0;
+    for (int i = lane; i < rows_all; i += 32) {
+        double nx, ny;
+        jacobi_rot(cs, sn, mp[i], mq[i], nx, ny);
+        mp[i] = nx;
+        mq[i] = ny;
+    }
+    return 1;
+}
+
+// blockDim = 32 * max(bs, 2): warp w owns cross pair w of an inner round.
+template <int NR>
+__global__ void __launch_bounds__(NR >= 4 ? 512 : 1024)
+jacobi_block_kernel(double* __restrict__ M, int64_t ld, int rows_dot, int rows_all, int l, int bs, int rpad, double tol,
+                    int* __restrict__ rotated, int* __restrict__ sweeps_out) {
+    extern __shared__ double xs[];                   // [2 * bs][rpad]: block I columns, then block J columns
+    cg::cluster_group cluster = cg::this_cluster();
+    const int C = (int)cluster.num_blocks(), c = (int)cluster.block_rank();
+    const int nblk = 2 * C;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = (int)(blockDim.x >> 5);
+    // valid columns of block blk (columns >= l do not exist)
+    auto ncols_of = [&](int blk) -> int {
+        const int left = l - blk * bs;
+        return left < 0 ? 0 : (left < bs ? left : bs);
+    };
+    // global block -> shared tile half (0 / 1) and back
+    auto load_block = [&](int blk, int half) {
+        const int nc = ncols_of(blk);
+        for (int j = warp; j < nc; j += nwarps) {
+            const double* src = M + (size_t)(blk * bs + j) * ld;
+            double* dst = xs + (size_t)(half * bs + j) * rpad;
+            for (int i = lane; i < rows_all; i += 32) dst[i] = __ldcg(src + i);
+        }
+    };
+    auto store_block = [&](int blk, int half) {
+        const int nc = ncols_of(blk);
+        for (int j = warp; j < nc; j += nwarps) {
+            double* dst = M + (size_t)(blk * bs + j) * ld;
+            const double* src = xs + (size_t)(half * bs + j) * rpad;
+            for (int i = lane; i < rows_all; i += 32) __stcg(dst + i, src[i]);
+        }
+    };
+    for (int i = threadIdx.x; i < 2 * bs * rpad; i += blockDim.x) xs[i] = 0.0;     // pad rows stay zero for good
+    __syncthreads();
+    int done = -1;
+    for (int sweep = 0; sweep < JF_MAX_SWEEPS; ++sweep) {
+        int nrot = 0;
+        // ---- (a) pairs inside my two blocks
+        {
+            const int I = 2 * c, J = 2 * c + 1;
+            const int ncI = ncols_of(I), ncJ = ncols_of(J);
+            load_block(I, 0);
+            load_block(J, 1);
+            __syncthreads();
+            const int npb = (bs + 1) / 2 * 2;                    // players per block (a dummy if bs is odd)
+            for (int round = 0; round < npb - 1; ++round) {
+                for (int slot = warp; slot < npb; slot += nwarps) {        // npb / 2 pairs per block, two blocks
+                    const int half = slot >= npb / 2;
+                    const int t = slot - half * (npb / 2);
+                    int p = rr_player_fast(t, round, npb), q = rr_player_fast(npb - 1 - t, round, npb);
+                    if (p > q) { const int tmp = p; p = q; q = tmp; }
+                    if (q < (half ? ncJ : ncI))
+                        nrot += jb_rotate_pair<NR>(xs + (size_t)(half * bs + p) * rpad, xs + (size_t)(half * bs + q) * rpad,
+                                                   rows_dot, rows_all, tol, lane);
+                }
+                __syncthreads();
+            }
+            store_block(I, 0);
+            store_block(J, 1);
+            cluster.sync();
+        }
+        // ---- (b) cross pairs of the block pairs, round-robin over the 2C blocks
+        for (int br = 0; br < nblk - 1; ++br) {
+            int I = rr_player(c, br, nblk), J = rr_player(nblk - 1 - c, br, nblk);
+            if (I > J) { const int tmp = I; I = J; J = tmp; }
+            const int ncI = ncols_of(I), ncJ = ncols_of(J);
+            load_block(I, 0);
+            load_block(J, 1);
+            __syncthreads();
+            int jq = warp;                                       // inner round r pairs column w of I with column (w + r) mod bs of J
+            for (int r = 0; r < bs; ++r) {
+                if (warp < ncI && jq < ncJ)
+                    nrot += jb_rotate_pair<NR>(xs + (size_t)warp * rpad, xs + (size_t)(bs + jq) * rpad, rows_dot, rows_all, tol,
+                                               lane);
+                if (++jq >= bs) jq -= bs;
+                __syncthreads();
+            }
+            store_block(I, 0);
+            store_block(J, 1);
+            cluster.sync();
+        }
+        // ---- convergence: rotations of this sweep over the whole cluster
+        if (lane == 0 && nrot) atomicAdd(rotated + sweep, nrot);
+        cluster.sync();
+        if (__ldcg(rotated + sweep) == 0) { done = sweep + 1; break; }
+    }
+    if (c == 0 && threadIdx.x == 0) *sweeps_out = done;
+}
+
 // sigma_j = ||m_j||, rank by descending sigma (ties: lower index first), write normalised
 // columns to U in sorted order.
 __global__ void jacobi_finalize_kernel(const double* __restrict__ M, int l, double* __restrict__ U,
@@ -213,6 +396,51 @@ static cudaError_t launch_jacobi_fused(gsi_ctx* ctx, int nctas, int wpc, double*
 
 void svd_check(gsi_ctx* ctx);
 
+// Block driver (svd.fused = 1); returns false when the two column blocks of a CTA do not fit its shared memory
+// or the cluster cannot be launched.
+static bool jacobi_sweeps_block(gsi_ctx* ctx, double* M, int64_t ld, int rows_dot, int rows_all, int ncols, double tol,
+                                bool defer_check) {
+    if (ncols < 4) return false;
+    int C = JF_MAX_CTAS;
+    while (C > 1 && 2 * C > ncols) C >>= 1;                  // at least one column per block
+    const int bs = (ncols + 2 * C - 1) / (2 * C);
+    if (bs > JB_MAX_BS) return false;
+    const int wpc = bs < 2 ? 2 : bs;                         // one warp per cross pair of an inner round
+    // rows per lane held in registers: 2 / 4 / 8 (then the column pitch is 32 * NR, zero padded); 0: streamed
+    int NR = rows_all <= 64 ? 2 : (rows_all <= 128 && wpc <= 16) ? 4 : (rows_all <= 256 && wpc <= 16) ? 8 : 0;
+    const int rpad = NR > 0 ? 32 * NR : (rows_all + 3) / 4 * 4 + 4;      // column pitch in shared memory
+    const size_t smem = (size_t)2 * bs * rpad * sizeof(double);
+    if (smem > (size_t)200 * 1024) return false;
+    const void* kfn = NR == 2 ? (const void*)jacobi_block_kernel<2> : NR == 4 ? (const void*)jacobi_block_kernel<4>
+                    : NR == 8 ? (const void*)jacobi_block_kernel<8> : (const void*)jacobi_block_kernel<0>;
+    GSI_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    GSI_CUDA(cudaMemsetAsync(ctx->jflags, 0, (JF_MAX_SWEEPS + 1) * sizeof(int), ctx->stream));
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)C);
+    cfg.blockDim = dim3((unsigned)wpc * 32);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = ctx->stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = (unsigned)C;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    int* rot = ctx->jflags;
+    int* swp = ctx->jflags + JF_MAX_SWEEPS;
+    void* args[] = {&M, &ld, &rows_dot, &rows_all, &ncols, (void*)&bs, (void*)&rpad, &tol, &rot, &swp};
+    const cudaError_t e = cudaLaunchKernelExC(&cfg, kfn, args);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        return false;
+    }
+    count_launch(ctx);
+    ctx->svd_pending = true;
+    if (!defer_check) svd_check(ctx);
+    return true;
+}
+
 // Single-launch driver; returns false when the problem does not fit one cluster.
 static bool jacobi_sweeps_fused(gsi_ctx* ctx, double* M, int64_t ld, int rows_dot, int rows_all, int ncols, int np,
                                 double tol, bool defer_check) {
@@ -245,11 +473,15 @@ void svd_check(gsi_ctx* ctx) {
     int h = 0;
     GSI_CUDA(cudaMemcpyAsync(&h, ctx->jflags + JF_MAX_SWEEPS, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
     GSI_CUDA(cudaStreamSynchronize(ctx->stream));
+    ctx->svd_last_sweeps = h;
     GSI_REQUIRE(h > 0, GSI_ERR_NO_CONVERGENCE, "Jacobi SVD did not converge in 60 sweeps");
 }
 
 void jacobi_sweeps(gsi_ctx* ctx, double* M, int64_t ld, int rows_dot, int rows_all, int ncols, bool defer_check) {
     const int np = (ncols + 1) / 2 * 2;
+    if (ctx->svd_fused == 1 &&
+        jacobi_sweeps_block(ctx, M, ld, rows_dot, rows_all, ncols, sqrt((double)rows_dot) * 2.220446049250313e-16, defer_check))
+        return;
     if (ctx->svd_fused &&
         jacobi_sweeps_fused(ctx, M, ld, rows_dot, rows_all, ncols, np, sqrt((double)rows_dot) * 2.220446049250313e-16,
                             defer_check))

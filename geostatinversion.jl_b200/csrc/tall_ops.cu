@@ -3,6 +3,9 @@
 // and the "tall x small" product expressed through the dense DMMA kernel.
 #include "common.cuh"
 #include "nb_list.h"
+#include <cstring>
+#include <thread>
+#include <vector>
 
 namespace gsi {
 
@@ -55,6 +58,34 @@ __global__ void tall_to_colblock_kernel(const double* __restrict__ tall, int64_t
 // driver's own staging of a pageable cudaMemcpy2DAsync ran at ~2.3 GB/s here (82 MB rga batch: 35 ms).
 static const size_t kPinBytes = (size_t)16 << 20;
 
+// Pageable source -> bounce buffer.  One core copies at 3-10 GB/s, less than half of what the DMA engine
+// moves, so slices of a few MB and more are split over a handful of threads.
+static void host_copy_rows(char* dst, const char* src, size_t nr, size_t width, size_t spitch) {
+    const size_t total = nr * width;
+    unsigned hw = std::thread::hardware_concurrency();
+    size_t nt = hw >= 16 ? 8 : hw >= 8 ? 4 : hw >= 4 ? 2 : 1;
+    if (total < ((size_t)4 << 20)) nt = 1;
+    auto copy_range = [=](size_t b0, size_t b1) {             // byte range of the packed destination
+        if (spitch == width) { memcpy(dst + b0, src + b0, b1 - b0); return; }
+        size_t b = b0;
+        while (b < b1) {
+            const size_t row = b / width, off = b - row * width;
+            const size_t len = (width - off < b1 - b) ? width - off : b1 - b;
+            memcpy(dst + b, src + row * spitch + off, len);
+            b += len;
+        }
+    };
+    if (nt <= 1) { copy_range(0, total); return; }
+    const size_t chunk = ((total + nt - 1) / nt + 4095) / 4096 * 4096;
+    std::vector<std::thread> th;
+    for (size_t t = 1; t < nt; ++t) {
+        const size_t b0 = t * chunk, b1 = (b0 + chunk < total) ? b0 + chunk : total;
+        if (b0 < total) th.emplace_back(copy_range, b0, b1);
+    }
+    copy_range(0, chunk < total ? chunk : total);
+    for (auto& x : th) x.join();
+}
+
 static void h2d_2d(gsi_ctx* ctx, void* dst, size_t dpitch, const void* src, size_t spitch, size_t width, size_t height) {
     if (width == 0 || height == 0) return;
     cudaPointerAttributes at;
@@ -77,8 +108,7 @@ static void h2d_2d(gsi_ctx* ctx, void* dst, size_t dpitch, const void* src, size
         GSI_CUDA(cudaEventSynchronize(ctx->pin_ev[b]));            // the DMA that last read this bounce buffer is done
         char* pb = static_cast<char*>(ctx->pin[b]);
         const char* sp = static_cast<const char*>(src) + r * spitch;
-        if (spitch == width) memcpy(pb, sp, nr * width);
-        else for (size_t i = 0; i < nr; ++i) memcpy(pb + i * width, sp + i * spitch, width);
+        host_copy_rows(pb, sp, nr, width, spitch);
         GSI_CUDA(cudaMemcpy2DAsync(static_cast<char*>(dst) + r * dpitch, dpitch, pb, width, width, nr, cudaMemcpyHostToDevice,
                                    ctx->stream));
         GSI_CUDA(cudaEventRecord(ctx->pin_ev[b], ctx->stream));

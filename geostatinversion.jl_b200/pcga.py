@@ -193,15 +193,19 @@ class LinearForwardModel:
     def __call__(self, s):
         return self.op.apply(np.asarray(s, dtype=np.float64))
 
+    def apply_batch_device(self, P):
+        """P: TALL DeviceMatrix n x c  ->  TALL DeviceMatrix nobs x c (caller frees)."""
+        return self.op.apply(P)
+
     def apply_batch(self, P):
         """P: TALL DeviceMatrix n x c  ->  host array nobs x c."""
-        Y = self.op.apply(P)
+        Y = self.apply_batch_device(P)
         out = Y.numpy()
         Y.free()
         return out
 
 
-MAX_XIS = 253      # the paramstorun batch [xis.., X, s, s] is one device iterate of at most 256 columns
+MAX_XIS = 1021     # the paramstorun batch [xis.., X, s, s] is one device iterate of at most 1024 columns
 
 
 def _xis_to_device(ctx, xis):
@@ -209,7 +213,7 @@ def _xis_to_device(ctx, xis):
         return xis, xis.shape[1], False
     if len(xis) > MAX_XIS:
         raise ValueError(f"pcgalsqr / pcgadirect / rga take at most {MAX_XIS} xis on the device path "
-                         f"(the batch of K+3 parameter vectors is one device iterate of <= 256 columns); got {len(xis)}")
+                         f"(the batch of K+3 parameter vectors is one device iterate of <= 1024 columns); got {len(xis)}")
     Zk = np.stack([np.asarray(x, dtype=np.float64) for x in xis], axis=1)
     return DeviceMatrix.from_host(ctx, Zk), Zk.shape[1], True
 
@@ -343,16 +347,33 @@ class _Sketch:
         self.ctx = ctx
         self.S = np.asfortranarray(S, dtype=np.float64)
         self.buf = DeviceMatrix.from_host(ctx, self.S, LAYOUT_COLMAJOR)
+        self._batch = None
+
+    def apply_device(self, Vd):
+        """S * V for a TALL device V (nobs x c) -> host array Nred x c."""
+        out = DeviceMatrix(self.ctx, self.S.shape[0], Vd.shape[1], LAYOUT_TALL)
+        try:
+            check(self.ctx._lib.gsi_sketch_apply(self.ctx._h, self.buf._h, Vd._h, out._h))
+            return out.numpy()
+        finally:
+            out.free()
 
     def apply(self, V):
         """S * V for host V (nobs x c or vector)."""
         V2 = _f64_colmajor(V)
         Vd = DeviceMatrix.from_host(self.ctx, V2)
-        out = DeviceMatrix(self.ctx, self.S.shape[0], V2.shape[1], LAYOUT_TALL)
-        check(self.ctx._lib.gsi_sketch_apply(self.ctx._h, self.buf._h, Vd._h, out._h))
-        res = out.numpy()
-        Vd.free(); out.free()
+        try:
+            res = self.apply_device(Vd)
+        finally:
+            Vd.free()
         return res[:, 0] if np.ndim(V) == 1 else res
+
+    def batch_buffer(self, nobs, c):
+        """Page-locked column-major staging array for the nobs x c batch of forward runs of one
+        iteration (reused across iterations: the upload is then a plain DMA, no bounce copy)."""
+        if self._batch is None or self._batch.shape != (nobs, c):
+            self._batch = self.ctx.pinned_empty((nobs, c))
+        return self._batch
 
     def cov(self, R):
         """S * R * S'."""
@@ -375,14 +396,21 @@ class _SketchedModel:
         return self.sk.apply(self.f(x))                         # x -> S * forwardmodel(x)
 
     def apply_batch(self, P):
+        if hasattr(self.f, "apply_batch_device"):
+            # declared linear model: H*P stays on the device, S*(H*P) follows without a host round trip
+            Vd = self.f.apply_batch_device(P)
+            try:
+                return self.sk.apply_device(Vd)
+            finally:
+                Vd.free()
         if hasattr(self.f, "apply_batch"):
             return self.sk.apply(self.f.apply_batch(P))
         Ph = P.numpy()
         V = None
-        for i in range(Ph.shape[1]):                            # assembled column-major: no transposing copy on upload
+        for i in range(Ph.shape[1]):                            # assembled column-major in page-locked memory
             v = np.asarray(self.f(np.ascontiguousarray(Ph[:, i])), dtype=np.float64)
             if V is None:
-                V = np.empty((v.shape[0], Ph.shape[1]), order="F")
+                V = self.sk.batch_buffer(v.shape[0], Ph.shape[1])
             V[:, i] = v
         return self.sk.apply(V)                                 # all K+3 sketches as one GEMM
 

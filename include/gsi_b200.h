@@ -112,10 +112,11 @@ int32_t gsi_ctx_phase_timing(gsi_ctx* ctx, double* ms_out8, int32_t reset);
  *   "kcov.epoch_shift"   epoch = 2^shift k-tiles of 32 points
  *   "svd.fused"          1 (default): the small Jacobi SVD (<= 512 columns) runs all sweeps in
  *                        one thread-block-cluster launch; 0: one launch per round (same rotations)
- *   "lu.panel"           1 (default): one cooperative launch per 16-column LU panel, the panel rows
- *                        resident in shared memory; 0: one launch pair per column (same pivots and
- *                        arithmetic, bit-identical L)
- *   "qr.panel"           1 (default): the same for the Householder QR panels; 0: launch pair per column
+ *   "lu.panel"           1 (default): one launch per 16-column LU panel, the panel rows resident in
+ *                        shared memory -- a single thread-block cluster for short iterates, a
+ *                        cooperative grid otherwise; 2: always the cooperative grid; 0: one launch
+ *                        pair per column (same pivots and arithmetic in all three, bit-identical L)
+ *   "qr.panel"           the same for the Householder QR panels (0 / 1 / 2)
  * The environment variables GSI_SWEEP="groups,div,hint[,window[,epoch_shift]]" and
  * GSI_OPTIONS="name=value,name=value" set the same knobs at context creation.         */
 int32_t gsi_ctx_set_option(gsi_ctx* ctx, const char* name, int64_t value);
@@ -125,6 +126,12 @@ int32_t gsi_ctx_get_option(gsi_ctx* ctx, const char* name, int64_t* value_out);
 int32_t gsi_buf_alloc(gsi_ctx* ctx, int32_t layout, int64_t rows, int64_t cols, gsi_buf** out);
 int32_t gsi_buf_free(gsi_buf* buf); /* idempotent on NULL, never throws (Julia finalizer) */
 int32_t gsi_buf_dims(const gsi_buf* buf, int64_t* rows, int64_t* cols);
+/* Page-locked host memory for arrays that are uploaded repeatedly (the batch of forward runs
+ * an rga iteration sketches, src/GeostatInversion.jl:102): uploads from such memory are plain
+ * DMA; any other (pageable) source is staged through the context's pinned bounce buffers.
+ * Julia shim: `unsafe_wrap(Array, Ptr{Float64}(p), dims)`; release with gsi_host_free.  */
+int32_t gsi_host_alloc(gsi_ctx* ctx, int64_t bytes, void** out);
+int32_t gsi_host_free(gsi_ctx* ctx, void* ptr); /* ptr NULL: no-op; ctx may be NULL */
 /* host (column-major, leading dimension ldh) <-> device, synchronous                 */
 int32_t gsi_buf_upload(gsi_buf* buf, const double* host, int64_t ldh);
 int32_t gsi_buf_download(const gsi_buf* buf, double* host, int64_t ldh);

@@ -118,6 +118,14 @@ function download(b::DeviceMatrix)
 	return A
 end
 
+"Matrix{Float64} in page-locked host memory (gsi_host_alloc): `upload!` from it is a plain DMA.  Release with `freepinned`."
+function pinnedmatrix(ctx::Context, rows::Integer, cols::Integer)
+	out = Ref{Ptr{Cvoid}}(C_NULL)
+	check(ccall((:gsi_host_alloc, LIB), Int32, (Ptr{Cvoid}, Int64, Ref{Ptr{Cvoid}}), ctx.h, 8 * max(1, rows * cols), out))
+	return unsafe_wrap(Array, Ptr{Float64}(out[]), (Int(rows), Int(cols)); own=false)
+end
+freepinned(ctx::Context, A::Matrix{Float64}) = check(ccall((:gsi_host_free, LIB), Int32, (Ptr{Cvoid}, Ptr{Cvoid}), ctx.h, pointer(A)))
+
 # A TALL device iterate holds at most 256 columns; wider host matrices go through in passes.
 const MAXCOLS = 256
 

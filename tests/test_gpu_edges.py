@@ -91,3 +91,27 @@ def test_device_resident_api(gsi):
     assert np.allclose(S[:25], oracle.singvals_from_Z(Z, 25), rtol=1e-12)
     before = ctx.launch_count(reset=True)
     assert before > 0
+
+
+def test_pinned_host_array_and_large_pageable_upload(gsi):
+    """gsi_host_alloc: a page-locked column-major array (plain DMA upload); and a pageable source large enough
+    to take the threaded bounce-buffer path with a pitched (row-block) source."""
+    ctx = gsi.default_context()
+    rng = np.random.default_rng(11)
+    P = ctx.pinned_empty((5000, 37))
+    assert P.flags.f_contiguous and P.shape == (5000, 37)
+    P[...] = rng.standard_normal(P.shape)
+    for layout in (gsi.LAYOUT_TALL, gsi.LAYOUT_COLMAJOR):
+        d = gsi.DeviceMatrix.from_host(ctx, P, layout)
+        assert np.array_equal(d.numpy(), P)
+        d.free()
+    del P                                          # releases the block (gsi_host_free)
+    A = rng.standard_normal((400000, 36))          # 115 MB: more rows than one staging block, slices of 16 MB
+    A = np.asfortranarray(A)
+    d = gsi.DeviceMatrix.from_host(ctx, A)
+    assert np.array_equal(d.numpy(), A)
+    d.free()
+    B = np.asfortranarray(rng.standard_normal((70000, 30)))
+    d = gsi.DeviceMatrix.from_host(ctx, B, gsi.LAYOUT_COLMAJOR)
+    assert np.array_equal(d.numpy(), B)
+    d.free()

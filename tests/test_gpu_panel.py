@@ -1,6 +1,7 @@
-"""The two drivers of the LU / QR panel factorisations must agree: the cooperative
-single-launch panel kernels (default, panel rows resident in shared memory) against the
-launch-per-column drivers of the first round, and both against the oracle's LAPACK calls
+"""The drivers of the LU / QR panel factorisations must agree: the single-launch panel kernels
+(panel rows resident in shared memory; option value 1 = a single thread-block cluster for short
+iterates / cooperative grid otherwise, 2 = always the cooperative grid) against the
+launch-per-column drivers of the first round (0), and all against the oracle's LAPACK calls
 (reference src/RandMatFact.jl:60-61,75-76 -> dgetrf / dgeqp3)."""
 import numpy as np
 import pytest
@@ -23,7 +24,8 @@ def _with_option(ctx, name, value, fn):
 # (n, l): single CTA; several CTAs; odd panel remainders; the widest iterate; more rows per CTA than
 # shared memory holds (overflow rows worked on in place: n > 148 * 1432)
 LU_SHAPES = [(64, 8), (40, 33), (300, 17), (1000, 60), (5000, 110), (20000, 210), (777, 256), (2049, 16),
-             (230000, 40), (3000, 300), (1500, 520)]      # the last two: iterates wider than 256 columns
+             (230000, 40), (3000, 300), (1500, 520),      # the last two: iterates wider than 256 columns
+             (10000, 110), (25088, 48), (26900, 20), (27100, 20)]   # one cluster of 16 CTAs; rows beyond its shared memory; just past it
 
 
 @pytest.mark.parametrize("n,l", LU_SHAPES)
@@ -33,7 +35,9 @@ def test_lu_panel_matches_per_column_and_oracle(gsi, n, l):
     Y = np.random.default_rng(n + l).standard_normal((n, l))
     L0 = _with_option(ctx, "lu.panel", 0, lambda: lu_L(Y))
     L1 = _with_option(ctx, "lu.panel", 1, lambda: lu_L(Y))
+    L2 = _with_option(ctx, "lu.panel", 2, lambda: lu_L(Y))
     assert np.array_equal(L0, L1)                       # same pivots, same arithmetic
+    assert np.array_equal(L0, L2)
     assert relerr(L1, oracle.lu_L_unpermuted(Y)) < 1e-10
 
 
@@ -52,17 +56,19 @@ def test_lu_panel_ties_and_zero_pivot(gsi):
         except gsi.SingularException as e:
             return None, e
     L1, e1 = _with_option(ctx, "lu.panel", 1, run)
+    L2, e2 = _with_option(ctx, "lu.panel", 2, run)
     L0, e0 = _with_option(ctx, "lu.panel", 0, run)
-    assert (e0 is None) == (e1 is None)
+    assert (e0 is None) == (e1 is None) == (e2 is None)
     if e0 is None:
-        assert np.array_equal(L0, L1)
+        assert np.array_equal(L0, L1) and np.array_equal(L0, L2)
     else:
-        assert str(e0) == str(e1)
+        assert str(e0) == str(e1) == str(e2)
     # integer-valued columns with many exact ties, non-singular
     rng = np.random.default_rng(1)
     T = rng.integers(-2, 3, size=(3000, 24)).astype(np.float64) + 8.0 * np.eye(3000, 24)
     L1 = _with_option(ctx, "lu.panel", 1, lambda: lu_L(T))
     assert np.array_equal(L1, _with_option(ctx, "lu.panel", 0, lambda: lu_L(T)))
+    assert np.array_equal(L1, _with_option(ctx, "lu.panel", 2, lambda: lu_L(T)))
     assert relerr(L1, oracle.lu_L_unpermuted(T)) < 1e-12
 
 
@@ -70,7 +76,7 @@ def test_lu_exact_zero_pivot_raises(gsi):
     from gsi_b200.pcga import lu_L
     Y = np.random.default_rng(2).standard_normal((500, 20))
     Y[:, 7] = 0.0
-    for panel in (1, 0):
+    for panel in (1, 2, 0):
         with pytest.raises(gsi.SingularException):
             _with_option(gsi.default_context(), "lu.panel", panel, lambda: lu_L(Y))
     with pytest.raises(oracle.randmatfact.SingularException):
@@ -92,14 +98,15 @@ def test_lu_nan_propagates(gsi):
     Y = np.random.default_rng(3).standard_normal((1000, 12))
     Y[417, 3] = np.nan
     masks = []
-    for panel in (1, 0):
+    for panel in (1, 2, 0):
         L = _with_option(gsi.default_context(), "lu.panel", panel, lambda: lu_L(Y))
         assert np.isnan(L).any()
         masks.append(np.isnan(L))
-    assert np.array_equal(masks[0], masks[1])
+    assert np.array_equal(masks[0], masks[1]) and np.array_equal(masks[0], masks[2])
 
 
-QR_SHAPES = [(64, 8), (1000, 60), (20000, 210), (300, 256), (5000, 33), (2049, 16), (230000, 24), (3000, 300), (1500, 520)]
+QR_SHAPES = [(64, 8), (1000, 60), (20000, 210), (300, 256), (5000, 33), (2049, 16), (230000, 24), (3000, 300), (1500, 520),
+             (10000, 110), (25088, 48), (27100, 20)]
 
 
 @pytest.mark.parametrize("n,l", QR_SHAPES)
@@ -114,6 +121,10 @@ def test_qr_panel(gsi, n, l):
     Q1, R1 = _with_option(ctx, "qr.panel", 1, lambda: qr_thinQ(Y, return_R=True))
     Q1b = _with_option(ctx, "qr.panel", 1, lambda: qr_thinQ(Y))
     assert np.array_equal(Q1, Q1b)                                  # deterministic
+    Q2, R2 = _with_option(ctx, "qr.panel", 2, lambda: qr_thinQ(Y, return_R=True))     # cooperative-grid transport
+    assert np.max(np.abs(Q2.T @ Q2 - np.eye(l))) < 1e-12
+    assert relerr(Q2 @ R2, Y) < 1e-13
+    assert relerr(R2, R0) < 1e-11 and relerr(Q2, Q0) < 1e-9
     assert np.max(np.abs(Q1.T @ Q1 - np.eye(l))) < 1e-12
     assert relerr(Q1 @ R1, Y) < 1e-13
     assert relerr(R1, R0) < 1e-11 and relerr(Q1, Q0) < 1e-9

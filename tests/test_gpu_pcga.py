@@ -250,6 +250,50 @@ def test_simpletestrga(gsi):
     assert relerr(popt2, pref2) < 1e-6      # measured 7.5e-8 (sketch-GEMM rounding amplified by 1/delta)
 
 
+def test_pcga_more_than_253_xis(gsi):
+    """the reference has no limit on the number of xis; the K+3 batch is a wide device iterate
+    (> 256 columns) -- one iteration against the oracle on the same xis, black-box and declared linear model."""
+    from gsi_b200.pcga import pcgalsqriteration, pcgadirectiteration, LinearForwardModel
+    K, N, nobs = 300, 1500, 80
+    rng = np.random.default_rng(300)
+    Z = np.linalg.qr(rng.standard_normal((N, K)))[0] * (2.0 ** (-np.arange(K) / 40.0))[None, :]
+    xis = [np.ascontiguousarray(Z[:, i]) for i in range(K)]
+    H = rng.standard_normal((nobs, N)) / np.sqrt(N)
+    truth = 1.5 + Z @ rng.standard_normal(K)
+    R = 1e-2 * np.ones(nobs)                                    # well-conditioned saddle-point system: LSQR converges
+    y = H @ truth + 1e-1 * rng.standard_normal(nobs)
+    X, s0 = np.ones(N), np.full(N, 1.5)
+    f = lambda s: H @ s                                         # noqa: E731
+    assert pc.paramstorun_bit_identical(gsi, s0, X, xis)
+    so = oracle.pcgalsqriteration(f, s0, X, xis, R, y, pc.DELTA, lsqr_kwargs=TIGHT)
+    assert relerr(pcgalsqriteration(f, s0, X, xis, R, y, pc.DELTA, lsqr_kwargs=TIGHT), so) < 1e-7
+    assert relerr(pcgalsqriteration(LinearForwardModel(H), s0, X, xis, R, y, pc.DELTA, lsqr_kwargs=TIGHT), so) < 1e-5
+    sd = pcgadirectiteration(f, s0, X, xis, R, y, pc.DELTA, lambda s, o: None)
+    sdo = oracle.pcgadirectiteration(f, s0, X, xis, R, y, pc.DELTA, lambda s, o: None)
+    assert relerr(sd, sdo) < 1e-5
+
+
+def test_rga_declared_linear_model_stays_on_device(gsi):
+    """rga with a LinearForwardModel: H*P and S*(H*P) never visit the host; same estimate as the black-box
+    path (whose batch is assembled in page-locked memory)."""
+    from gsi_b200.pcga import LinearForwardModel
+    M, N, Nred = 6, 900, 300
+    rng = np.random.default_rng(77)
+    H = rng.standard_normal((N, N)) / np.sqrt(N) + np.eye(N)
+    Q = np.exp(-np.abs(np.subtract.outer(np.arange(N), np.arange(N))) / 40.0)
+    Omega = rng.standard_normal((N, M + 10))
+    xis = gsi.getxis(Q, M, 10, Omega=Omega)
+    truep = 3.0 + np.stack(xis, axis=1) @ rng.standard_normal(M)
+    R = 1e-6 * np.ones(N)
+    yobs = H @ truep + 1e-3 * rng.standard_normal(N)
+    X, p0 = np.ones(N), np.full(N, 3.0)
+    S = rng.standard_normal((Nred, N)) / np.sqrt(N)
+    pa = gsi.rga(LinearForwardModel(H), p0, X, xis, R, yobs, S, pcgafunc=gsi.pcgalsqr)
+    pb = gsi.rga(lambda s: H @ s, p0, X, xis, R, yobs, S, pcgafunc=gsi.pcgalsqr)
+    assert np.linalg.norm(pa - truep) / np.linalg.norm(truep) < 2e-2
+    assert relerr(pa, pb) < 1e-5
+
+
 def test_sketch_products(gsi):
     rng = np.random.default_rng(9)
     Nred, nobs = 300, 1500
