@@ -207,20 +207,31 @@ struct LuPanelParams {
     int cap;
 };
 
-__device__ __forceinline__ void lp_warp_best(double& bv, double& bi) {
-    for (int o = 1; o < 32; o <<= 1) {
-        const double ov = __shfl_xor_sync(0xffffffffu, bv, o), oi = __shfl_xor_sync(0xffffffffu, bi, o);
-        if (cand_better(ov, oi, bv, bi)) { bv = ov; bi = oi; }
-    }
+// Pivot candidates inside the panel kernel are (key, row): key = bit pattern of |value| + 1 (non-negative doubles
+// order like unsigned integers; NaN counts as +inf; key 0 = no candidate), row = global row index (< 2^31).
+// "better" = larger key, then smaller row -- LAPACK's idamax rule.  A warp arg-max is three redux.sync
+// instructions (high word, low word, row) instead of a five-stage shuffle butterfly on two doubles.
+__device__ __forceinline__ unsigned long long lp_key(double v) {
+    return (unsigned long long)__double_as_longlong(cand_abs(v)) + 1ull;
+}
+__device__ __forceinline__ void lp_warp_argmax(unsigned long long& key, int& row) {
+    const unsigned int hi = (unsigned int)(key >> 32), lo = (unsigned int)key;
+    const unsigned int mh = __reduce_max_sync(0xffffffffu, hi);
+    const unsigned int ml = __reduce_max_sync(0xffffffffu, hi == mh ? lo : 0u);
+    const bool mine = (hi == mh) && (lo == ml);
+    const unsigned int mr = __reduce_min_sync(0xffffffffu, mine ? (unsigned int)row : 0xffffffffu);
+    key = ((unsigned long long)mh << 32) | ml;
+    row = (int)mr;
 }
 
 template <int CL>
 __global__ void __launch_bounds__(LP_THREADS, 1) lu_panel_kernel(const LuPanelParams p) {
     extern __shared__ double sm[];                 // [cap][LP_PITCH]
     __shared__ double s_xrec[CL ? 2 * kPxchClusterMax * kPxchRec : 1];   // CL = 1: everybody's records, by parity
-    __shared__ double s_bv[LP_WARPS], s_bi[LP_WARPS];
+    __shared__ unsigned long long s_wkey[LP_WARPS];
+    __shared__ int s_wrow[LP_WARPS];
     __shared__ double s_prow[LU_PB], s_krow[LU_PB];
-    __shared__ double s_win[2];                    // pivot row index
+    __shared__ int s_win;                          // CL = 0: pivot row index
     __shared__ int s_piv[LU_PB];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, sub = lane & 3, rslot = tid >> 2;
     const int G = (int)gridDim.x, b = (int)blockIdx.x;       // CL = 1: the grid is one cluster, block rank == blockIdx.x
@@ -236,18 +247,10 @@ __global__ void __launch_bounds__(LP_THREADS, 1) lu_panel_kernel(const LuPanelPa
         return li < p.cap ? sm + (size_t)li * LP_PITCH : Ypan + (r0 + li) * ld;
     };
     // entry j of the record CTA q published for column parity par
+    //   [0] key (bit pattern)  [1] row  [4 .. 20) the candidate row's panel entries  [20 .. 36) row k's entries (owner only)
     auto rec_rd = [&](int par, int q, int j) -> double {
         if (CL) return s_xrec[(par * kPxchClusterMax + q) * kPxchRec + j];
         return __ldcg(p.recs + ((size_t)par * kPxchMaxCtas + q) * kPxchRec + j);
-    };
-    auto rec_wr = [&](int par, int j, double v) {
-        if (CL) {
-            cg::cluster_group cluster = cg::this_cluster();
-            double* mine = s_xrec + (par * kPxchClusterMax + b) * kPxchRec + j;
-            for (int d = 0; d < G; ++d) *cluster.map_shared_rank(mine, d) = v;
-        } else {
-            p.recs[((size_t)par * kPxchMaxCtas + b) * kPxchRec + j] = v;
-        }
     };
     auto barrier = [&]() {
         if (CL) cg::this_cluster().sync();
@@ -268,103 +271,100 @@ __global__ void __launch_bounds__(LP_THREADS, 1) lu_panel_kernel(const LuPanelPa
     __syncthreads();
     if (CL) cg::this_cluster().sync();             // every CTA of the cluster runs before anybody pushes a record into it
 
-    // block arg-max of (bv, bi) -> my record of column step c: candidate + its row, and row `col` if I own it
-    auto publish = [&](int col, int c, double bv, double bi) {
+    // block arg-max of my (key, row) -> my record of column step c: candidate + its row, and row `col` if I own it
+    auto publish = [&](int col, int c, unsigned long long key, int row) {
         const int par = c & 1;
-        lp_warp_best(bv, bi);
-        if (lane == 0) { s_bv[warp] = bv; s_bi[warp] = bi; }
+        lp_warp_argmax(key, row);
+        if (lane == 0) { s_wkey[warp] = key; s_wrow[warp] = row; }
         __syncthreads();                                   // also: all rows of this CTA are up to date
+        // every warp reduces the warp candidates (identically)
+        key = lane < LP_WARPS ? s_wkey[lane] : 0ull;
+        row = lane < LP_WARPS ? s_wrow[lane] : 0x7fffffff;
+        lp_warp_argmax(key, row);
+        const bool own_col = col >= r0 && col < r1;
         if (CL) {
-            // every warp reduces the warp candidates (identically); warp w pushes the record into CTA w's copy
-            bv = lane < LP_WARPS ? s_bv[lane] : -1.0;
-            bi = lane < LP_WARPS ? s_bi[lane] : 0.0;
-            lp_warp_best(bv, bi);
+            // warp w pushes the record into CTA w's copy
             if (warp < G) {
                 double* dst = cg::this_cluster().map_shared_rank(s_xrec + (par * kPxchClusterMax + b) * kPxchRec, warp);
-                if (lane == 0) { dst[0] = bv; dst[1] = bi; }
-                if (bv >= 0.0 && lane < pb) dst[4 + lane] = rowp((int)((int64_t)bi - r0))[lane];
-                if (col >= r0 && col < r1 && lane >= 16 && lane < 16 + pb)
-                    dst[4 + LU_PB + lane - 16] = rowp((int)(col - r0))[lane - 16];
+                if (lane == 0) { dst[0] = __longlong_as_double((long long)key); dst[1] = (double)row; }
+                if (key != 0ull && lane < pb) dst[4 + lane] = rowp((int)((int64_t)row - r0))[lane];
+                if (own_col && lane >= 16 && lane < 16 + pb) dst[4 + LU_PB + lane - 16] = rowp((int)(col - r0))[lane - 16];
             }
         } else if (warp == 0) {
-            bv = lane < LP_WARPS ? s_bv[lane] : -1.0;
-            bi = lane < LP_WARPS ? s_bi[lane] : 0.0;
-            lp_warp_best(bv, bi);
-            if (lane == 0) { rec_wr(par, 0, bv); rec_wr(par, 1, bi); }
-            if (bv >= 0.0 && lane < pb) rec_wr(par, 4 + lane, rowp((int)((int64_t)bi - r0))[lane]);
-        } else if (warp == 1) {
-            if (col >= r0 && col < r1 && lane < pb) rec_wr(par, 4 + LU_PB + lane, rowp((int)(col - r0))[lane]);
+            double* dst = p.recs + ((size_t)par * kPxchMaxCtas + b) * kPxchRec;
+            if (lane == 0) { dst[0] = __longlong_as_double((long long)key); dst[1] = (double)row; }
+            if (key != 0ull && lane < pb) dst[4 + lane] = rowp((int)((int64_t)row - r0))[lane];
+            if (own_col && lane >= 16 && lane < 16 + pb) dst[4 + LU_PB + lane - 16] = rowp((int)(col - r0))[lane - 16];
         }
         barrier();                                         // every CTA's record of this column step is visible
     };
 
     // ---- candidates of the first column of the panel
     {
-        double bv = -1.0, bi = 0.0;
+        unsigned long long key = 0ull;
+        int row = 0x7fffffff;
         if (sub == 0) {
             for (int li = lfirst + rslot; li < nown; li += LP_THREADS / 4) {
-                const double v = cand_abs(rowp(li)[0]);
-                const double gi = (double)(r0 + li);
-                if (cand_better(v, gi, bv, bi)) { bv = v; bi = gi; }
+                const unsigned long long kk = lp_key(rowp(li)[0]);
+                if (kk > key) { key = kk; row = (int)(r0 + li); }
             }
         }
-        publish(p.ps, 0, bv, bi);
+        publish(p.ps, 0, key, row);
     }
 
     for (int k = p.ps; k < p.pe; ++k) {
         const int c = k - p.ps;
         const int par = c & 1;
         const int owner_k = (int)(k / p.R);
-        // ---- global pivot: the G candidates reduced the same way everywhere (CTA order, first maximum wins).
-        //      CL = 1: every warp does it for itself from the shared-memory records (no block barrier, no staging);
+        // ---- global pivot: the G candidates reduced the same way everywhere (largest key, then smallest row).
+        //      CL = 1: every warp does it for itself from the shared-memory records (no staging);
         //      CL = 0: warp 0 reads the records from L2 and stages the pivot row / row k for the block.
-        int64_t piv;
+        int piv;
         const double* prow;                                 // the pivot row's panel entries
         const double* krow;                                 // row k's panel entries before the interchange
         if (CL) {
-            double bv = lane < G ? rec_rd(par, lane, 0) : -1.0;
-            double bi = lane < G ? rec_rd(par, lane, 1) : 0.0;
-            int bw = lane;
-            if (!(bv >= 0.0)) bv = -1.0;                    // (no candidate)
-            for (int o = 1; o < 32; o <<= 1) {
-                const double ov = __shfl_xor_sync(0xffffffffu, bv, o), oi = __shfl_xor_sync(0xffffffffu, bi, o);
-                const int ow = __shfl_xor_sync(0xffffffffu, bw, o);
-                if (cand_better(ov, oi, bv, bi)) { bv = ov; bi = oi; bw = ow; }
-            }
+            unsigned long long key = lane < G ? (unsigned long long)__double_as_longlong(rec_rd(par, lane, 0)) : 0ull;
+            int row = lane < G ? (int)rec_rd(par, lane, 1) : 0x7fffffff;
+            const unsigned long long mykey = key;
+            const int myrow = row;
+            lp_warp_argmax(key, row);
+            const unsigned int who = __ballot_sync(0xffffffffu, mykey == key && myrow == row && lane < G);
             krow = s_xrec + (par * kPxchClusterMax + owner_k) * kPxchRec + 4 + LU_PB;
-            if (bv < 0.0) { bi = (double)k; prow = krow; }  // no row left (cannot happen for n >= l): no interchange
-            else prow = s_xrec + (par * kPxchClusterMax + bw) * kPxchRec + 4;
-            piv = (int64_t)bi;
-            if (tid == 0) s_piv[c] = (int)bi;
+            if (key == 0ull) { row = k; prow = krow; }      // no row left (cannot happen for n >= l): no interchange
+            else prow = s_xrec + (par * kPxchClusterMax + (__ffs(who) - 1)) * kPxchRec + 4;
+            piv = row;
+            if (tid == 0) s_piv[c] = piv;
         } else {
             if (warp == 0) {
-                double cv[kPxchMaxCtas / 32], ci[kPxchMaxCtas / 32];
+                unsigned long long key = 0ull;
+                int row = 0x7fffffff, bw = 0;
+                double kv[kPxchMaxCtas / 32], rv[kPxchMaxCtas / 32];
 #pragma unroll
                 for (int it = 0; it < kPxchMaxCtas / 32; ++it) {          // all loads in flight before the first compare
                     const int q = lane + 32 * it;
-                    cv[it] = q < G ? rec_rd(par, q, 0) : -1.0;
-                    ci[it] = q < G ? rec_rd(par, q, 1) : 0.0;
+                    kv[it] = q < G ? rec_rd(par, q, 0) : 0.0;
+                    rv[it] = q < G ? rec_rd(par, q, 1) : 0.0;
                 }
-                double bv = -1.0, bi = 0.0;
-                int bw = 0;
 #pragma unroll
                 for (int it = 0; it < kPxchMaxCtas / 32; ++it) {
-                    if (cv[it] >= 0.0 && cand_better(cv[it], ci[it], bv, bi)) { bv = cv[it]; bi = ci[it]; bw = lane + 32 * it; }
+                    const unsigned long long kk = (lane + 32 * it < G) ? (unsigned long long)__double_as_longlong(kv[it]) : 0ull;
+                    const int rr = (int)rv[it];
+                    if (kk > key || (kk == key && kk != 0ull && rr < row)) { key = kk; row = rr; bw = lane + 32 * it; }
                 }
-                for (int o = 1; o < 32; o <<= 1) {
-                    const double ov = __shfl_xor_sync(0xffffffffu, bv, o), oi = __shfl_xor_sync(0xffffffffu, bi, o);
-                    const int ow = __shfl_xor_sync(0xffffffffu, bw, o);
-                    if (cand_better(ov, oi, bv, bi)) { bv = ov; bi = oi; bw = ow; }
-                }
-                if (bv < 0.0) { bi = (double)k; }            // no row left (cannot happen for n >= l): no interchange
+                const unsigned long long mykey = key;
+                const int myrow = row;
+                lp_warp_argmax(key, row);
+                const unsigned int who = __ballot_sync(0xffffffffu, mykey == key && myrow == row);
+                bw = __shfl_sync(0xffffffffu, bw, __ffs(who) - 1);
+                if (key == 0ull) row = k;                    // no row left (cannot happen for n >= l): no interchange
                 if (lane < pb) {
                     s_krow[lane] = rec_rd(par, owner_k, 4 + LU_PB + lane);
-                    s_prow[lane] = bv >= 0.0 ? rec_rd(par, bw, 4 + lane) : s_krow[lane];
+                    s_prow[lane] = key != 0ull ? rec_rd(par, bw, 4 + lane) : s_krow[lane];
                 }
-                if (lane == 0) { s_win[0] = bi; s_piv[c] = (int)bi; }
+                if (lane == 0) { s_win = row; s_piv[c] = row; }
             }
             __syncthreads();
-            piv = (int64_t)s_win[0];
+            piv = s_win;
             prow = s_prow;
             krow = s_krow;
         }
@@ -375,60 +375,62 @@ __global__ void __launch_bounds__(LP_THREADS, 1) lu_panel_kernel(const LuPanelPa
         } else {
             rpiv = 1.0 / pivot;
         }
-        const bool use_recip = fabs(pivot) >= 2.2250738585072014e-308;       // dgetf2: sfmin
-        // ---- row interchange inside the panel.  Row k receives the pivot row (its owner writes it; nobody reads
-        //      row k again in this panel).  Row piv receives old row k: CL = 1 lazily, by the lanes that eliminate
-        //      it below; CL = 0 by its owner here, followed by a block barrier.
+        // LAPACK dgetf2: multiply by the reciprocal when |pivot| >= sfmin, divide otherwise; a zero pivot leaves the column
+        const int mode = pivot == 0.0 ? 2 : (fabs(pivot) >= 2.2250738585072014e-308 ? 0 : 1);
+        // my four columns: the pivot row's entries, and which of them this step updates
+        double pr[4];
+        bool act[4];
+#pragma unroll
+        for (int cc = 0; cc < 4; ++cc) {
+            const int j = sub + 4 * cc;
+            act[cc] = j > c && j < pb;
+            pr[cc] = act[cc] ? prow[j] : 0.0;
+        }
+        const int ncc = (c + 1) >> 2, nsub = (c + 1) & 3;                    // the next column lives in lane sub == nsub, slot ncc
+        const bool has_next = (c + 1 < pb) && sub == nsub;
+        // ---- row interchange inside the panel, each row by its owner
         if (piv != k) {
             if (tid < pb) {
                 if (k >= r0 && k < r1) rowp((int)(k - r0))[tid] = prow[tid];
-            } else if (!CL && tid >= 32 && tid < 32 + pb) {
+            } else if (tid >= 32 && tid < 32 + pb) {
                 if (piv >= r0 && piv < r1) rowp((int)(piv - r0))[tid - 32] = krow[tid - 32];
             }
-            if (!CL) __syncthreads();
+            __syncthreads();
         }
         // ---- elimination of my rows below k, candidates for column k+1
-        double bv = -1.0, bi = 0.0;
-        double pr[4];                                               // the pivot row entries of my four columns
-#pragma unroll
-        for (int cc = 0; cc < 4; ++cc) pr[cc] = (sub + 4 * cc < pb) ? prow[sub + 4 * cc] : 0.0;
-        // row = my local row li; lazy: it is row piv of a CL = 1 step and still holds the pivot row (takes krow's values)
+        unsigned long long bkey = 0ull;
+        int brow = 0x7fffffff;
+        // (warp-uniform trip counts and full-mask warp primitives: partial-mask variants compile to divergence-safe
+        //  sequences that cost more than the predicated tail iteration)
         auto eliminate_row = [&](double* row, int li, bool valid) {
-            const bool lazy = CL && valid && piv != k && (r0 + li == piv);
-            const double a = valid ? (lazy ? krow[c] : row[c]) : 0.0;
+            const double a = valid ? row[c] : 0.0;
             __syncwarp();                                   // all four lanes of a row have read a before lane 0 replaces it
-            if (valid) {
-                double m;
-                if (pivot == 0.0) m = a;
-                else m = use_recip ? a * rpiv : a / pivot;
-                if (sub == 0) row[c] = m;
+            const double m = mode == 0 ? a * rpiv : (mode == 1 ? a / pivot : a);
+            if (valid && sub == 0) row[c] = m;
+            double nextv = 0.0;
 #pragma unroll
-                for (int cc = 0; cc < 4; ++cc) {
-                    const int j = sub + 4 * cc;
-                    if (j > c && j < pb) {
-                        const double v = fma(-m, pr[cc], lazy ? krow[j] : row[j]);
-                        row[j] = v;
-                        if (j == c + 1) {
-                            const double av = cand_abs(v);
-                            const double gi = (double)(r0 + li);
-                            if (cand_better(av, gi, bv, bi)) { bv = av; bi = gi; }
-                        }
-                    } else if (lazy && j < c) {
-                        row[j] = krow[j];                   // the L part of old row k moves along
-                    }
+            for (int cc = 0; cc < 4; ++cc) {
+                if (valid && act[cc]) {
+                    const double v = fma(-m, pr[cc], row[sub + 4 * cc]);
+                    row[sub + 4 * cc] = v;
+                    if (cc == ncc) nextv = v;
                 }
+            }
+            if (valid && has_next) {
+                const unsigned long long kk = lp_key(nextv);
+                if (kk > bkey) { bkey = kk; brow = (int)(r0 + li); }
             }
         };
         const int lstart = (k + 1 > r0) ? (int)((k + 1 - r0 < nown) ? k + 1 - r0 : nown) : 0;
-        for (int base = lstart; base < nres; base += LP_THREADS / 4) {      // rows resident in shared memory (warp-uniform trip count)
+        for (int base = lstart; base < nres; base += LP_THREADS / 4) {       // rows resident in shared memory
             const int li = base + rslot;
             eliminate_row(sm + (size_t)(li < nres ? li : 0) * LP_PITCH, li, li < nres);
         }
-        for (int base = (nres > lstart ? nres : lstart); base < nown; base += LP_THREADS / 4) {  // overflow rows, in place
+        for (int base = (nres > lstart ? nres : lstart); base < nown; base += LP_THREADS / 4) {   // overflow rows, in place
             const int li = base + rslot;
             eliminate_row(Ypan + (r0 + (li < nown ? li : 0)) * ld, li, li < nown);
         }
-        if (k + 1 < p.pe) publish(k + 1, c + 1, bv, bi);
+        if (k + 1 < p.pe) publish(k + 1, c + 1, bkey, brow);
     }
     __syncthreads();
     // ---- write my resident rows back

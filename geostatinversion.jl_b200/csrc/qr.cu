@@ -395,32 +395,40 @@ __global__ void __launch_bounds__(QPK_THREADS, 1) qr_panel_kernel(const QrPanelP
         double psum[4] = {0.0, 0.0, 0.0, 0.0};
         const int lstart = first_local((int64_t)k + 1);
         const int slot = c + 1;                              // panel slot of the next column
+        const int li_top = (k + 1 >= r0 && k + 1 < r1) ? (int)(k + 1 - r0) : -1;     // row k+1 itself takes no part in the dots
+        const int src_lane = (lane & ~3) | (slot & 3);
+        bool act[4];
+#pragma unroll
+        for (int cc = 0; cc < 4; ++cc) act[cc] = (sub + 4 * cc > c) && (sub + 4 * cc < pb);
+        const bool has_c = (sub == (c & 3));                 // my slot (c >> 2) is column c itself
+        // (warp-uniform trip counts and full-mask warp primitives: partial-mask variants compile to divergence-safe
+        //  sequences that cost more than the predicated tail iteration)
         auto update_row = [&](double* row, int li, bool valid) {
             double nv[4] = {0.0, 0.0, 0.0, 0.0};
             const double a = valid ? row[c] : 0.0;
             __syncwarp();                                   // all four lanes of a row have read a before it is replaced
-            if (valid) {
-                const double v = scale * a;
+            const double v = scale * a;
 #pragma unroll
-                for (int cc = 0; cc < 4; ++cc) {
-                    const int j = sub + 4 * cc;
-                    if (j >= c && j < pb) {
-                        nv[cc] = (j == c) ? v : row[j] - v * twv[cc];
-                        row[j] = nv[cc];
-                    }
+            for (int cc = 0; cc < 4; ++cc) {
+                if (valid && act[cc]) {
+                    nv[cc] = row[sub + 4 * cc] - v * twv[cc];
+                    row[sub + 4 * cc] = nv[cc];
+                } else if (valid && has_c && cc == (c >> 2)) {
+                    nv[cc] = v;
+                    row[c] = v;
                 }
             }
             double mine = 0.0;
 #pragma unroll
             for (int cc = 0; cc < 4; ++cc)
                 if (cc == (slot >> 2)) mine = nv[cc];
-            const double ynext = __shfl_sync(0xffffffffu, mine, (lane & ~3) | (slot & 3));
-            if (valid && r0 + li > (int64_t)k + 1) {
+            const double ynext = __shfl_sync(0xffffffffu, mine, src_lane);
+            if (valid && li != li_top) {
 #pragma unroll
                 for (int cc = 0; cc < 4; ++cc) psum[cc] = fma(ynext, nv[cc], psum[cc]);
             }
         };
-        for (int base = lstart; base < nres; base += QPK_THREADS / 4) {      // rows resident in shared memory (warp-uniform trip count)
+        for (int base = lstart; base < nres; base += QPK_THREADS / 4) {      // rows resident in shared memory
             const int li = base + rslot;
             update_row(sm + (size_t)(li < nres ? li : 0) * QPK_PITCH, li, li < nres);
         }
