@@ -257,49 +257,73 @@ __device__ __forceinline__ int jb_rotate_pair(double* __restrict__ mp, double* _
 }
 
 // blockDim = 32 * max(bs, 2): warp w owns cross pair w of an inner round.
+// The column blocks never return to global memory between stages: a CTA works on a shared-memory tile
+// (two blocks) and, when a stage is done, PUSHES each of its blocks into the tile of the CTA that owns it in
+// the next stage (distributed shared memory, double-buffered tiles) -- one cluster barrier per stage and no
+// global round trip (the first version stored / fenced / reloaded the blocks through L2: about half of its
+// time at l = 110).  Global memory is read once at the start and written once at the end.
 template <int NR>
 __global__ void __launch_bounds__(NR >= 4 ? 512 : 1024)
 jacobi_block_kernel(double* __restrict__ M, int64_t ld, int rows_dot, int rows_all, int l, int bs, int rpad, double tol,
                     int* __restrict__ rotated, int* __restrict__ sweeps_out) {
-    extern __shared__ double xs[];                   // [2 * bs][rpad]: block I columns, then block J columns
+    extern __shared__ double xs_all[];               // [2 tiles][2 * bs][rpad]: block I columns, then block J columns
     cg::cluster_group cluster = cg::this_cluster();
     const int C = (int)cluster.num_blocks(), c = (int)cluster.block_rank();
     const int nblk = 2 * C;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = (int)(blockDim.x >> 5);
+    const int tile = 2 * bs * rpad;
+    const int rcopy = NR > 0 ? rpad : rows_all;      // rows moved per column (the zero pad rows travel along)
     // valid columns of block blk (columns >= l do not exist)
     auto ncols_of = [&](int blk) -> int {
         const int left = l - blk * bs;
         return left < 0 ? 0 : (left < bs ? left : bs);
     };
-    // global block -> shared tile half (0 / 1) and back
-    auto load_block = [&](int blk, int half) {
-        const int nc = ncols_of(blk);
+    // stage -1: intra-block stage (CTA c owns blocks 2c, 2c+1); stage br >= 0: cross stage br of the round-robin.
+    // Owner CTA and tile half of block X in a stage:
+    auto owner_of = [&](int X, int stage, int& cta, int& half) {
+        if (stage < 0) { cta = X >> 1; half = X & 1; return; }
+        int i = 0;                                   // position of X in round `stage`
+        if (X != 0) {
+            int x = (X - 1 - stage) % (nblk - 1);
+            if (x < 0) x += nblk - 1;
+            i = x + 1;
+        }
+        const int partner = rr_player(nblk - 1 - i, stage, nblk);
+        cta = i < C ? i : nblk - 1 - i;
+        half = X < partner ? 0 : 1;
+    };
+    for (int i = threadIdx.x; i < 2 * tile; i += blockDim.x) xs_all[i] = 0.0;      // pad rows stay zero for good
+    __syncthreads();
+    int cur = 0;
+    // ---- the only read of the matrix: my two blocks of the first (intra) stage
+    for (int half = 0; half < 2; ++half) {
+        const int blk = 2 * c + half, nc = ncols_of(blk);
         for (int j = warp; j < nc; j += nwarps) {
             const double* src = M + (size_t)(blk * bs + j) * ld;
-            double* dst = xs + (size_t)(half * bs + j) * rpad;
+            double* dst = xs_all + (size_t)(half * bs + j) * rpad;
             for (int i = lane; i < rows_all; i += 32) dst[i] = __ldcg(src + i);
         }
-    };
-    auto store_block = [&](int blk, int half) {
+    }
+    cluster.sync();                                  // every CTA of the cluster runs (and has zeroed its tiles) before anybody pushes into it
+    // push the block in tile half `half` of my current tile to its owner in `next_stage`
+    auto push_block = [&](int blk, int half, int next_stage) {
         const int nc = ncols_of(blk);
-        for (int j = warp; j < nc; j += nwarps) {
-            double* dst = M + (size_t)(blk * bs + j) * ld;
-            const double* src = xs + (size_t)(half * bs + j) * rpad;
-            for (int i = lane; i < rows_all; i += 32) __stcg(dst + i, src[i]);
-        }
+        if (nc == 0) return;
+        int cta, dhalf;
+        owner_of(blk, next_stage, cta, dhalf);
+        const double* src0 = xs_all + (size_t)cur * tile + (size_t)half * bs * rpad;
+        double* dst0 = cluster.map_shared_rank(xs_all + (size_t)(cur ^ 1) * tile + (size_t)dhalf * bs * rpad, cta);
+        for (int j = warp; j < nc; j += nwarps)
+            for (int i = lane; i < rcopy; i += 32) dst0[(size_t)j * rpad + i] = src0[(size_t)j * rpad + i];
     };
-    for (int i = threadIdx.x; i < 2 * bs * rpad; i += blockDim.x) xs[i] = 0.0;     // pad rows stay zero for good
-    __syncthreads();
     int done = -1;
     for (int sweep = 0; sweep < JF_MAX_SWEEPS; ++sweep) {
         int nrot = 0;
         // ---- (a) pairs inside my two blocks
         {
+            double* xs = xs_all + (size_t)cur * tile;
             const int I = 2 * c, J = 2 * c + 1;
             const int ncI = ncols_of(I), ncJ = ncols_of(J);
-            load_block(I, 0);
-            load_block(J, 1);
-            __syncthreads();
             const int npb = (bs + 1) / 2 * 2;                    // players per block (a dummy if bs is odd)
             for (int round = 0; round < npb - 1; ++round) {
                 for (int slot = warp; slot < npb; slot += nwarps) {        // npb / 2 pairs per block, two blocks
@@ -313,18 +337,17 @@ jacobi_block_kernel(double* __restrict__ M, int64_t ld, int rows_dot, int rows_a
                 }
                 __syncthreads();
             }
-            store_block(I, 0);
-            store_block(J, 1);
+            push_block(I, 0, 0);
+            push_block(J, 1, 0);
             cluster.sync();
+            cur ^= 1;
         }
         // ---- (b) cross pairs of the block pairs, round-robin over the 2C blocks
         for (int br = 0; br < nblk - 1; ++br) {
+            double* xs = xs_all + (size_t)cur * tile;
             int I = rr_player(c, br, nblk), J = rr_player(nblk - 1 - c, br, nblk);
             if (I > J) { const int tmp = I; I = J; J = tmp; }
             const int ncI = ncols_of(I), ncJ = ncols_of(J);
-            load_block(I, 0);
-            load_block(J, 1);
-            __syncthreads();
             int jq = warp;                                       // inner round r pairs column w of I with column (w + r) mod bs of J
             for (int r = 0; r < bs; ++r) {
                 if (warp < ncI && jq < ncJ)
@@ -333,14 +356,27 @@ jacobi_block_kernel(double* __restrict__ M, int64_t ld, int rows_dot, int rows_a
                 if (++jq >= bs) jq -= bs;
                 __syncthreads();
             }
-            store_block(I, 0);
-            store_block(J, 1);
+            const int next_stage = (br + 1 < nblk - 1) ? br + 1 : -1;
+            push_block(I, 0, next_stage);
+            push_block(J, 1, next_stage);
+            if (br + 1 == nblk - 1 && lane == 0 && nrot) atomicAdd(rotated + sweep, nrot);   // rotations of this sweep
             cluster.sync();
+            cur ^= 1;
         }
-        // ---- convergence: rotations of this sweep over the whole cluster
-        if (lane == 0 && nrot) atomicAdd(rotated + sweep, nrot);
-        cluster.sync();
+        // ---- convergence: rotations of this sweep over the whole cluster (the adds precede the last barrier)
         if (__ldcg(rotated + sweep) == 0) { done = sweep + 1; break; }
+    }
+    // ---- the only write: after the last stage every CTA holds blocks 2c, 2c+1 again
+    {
+        const double* xs = xs_all + (size_t)cur * tile;
+        for (int half = 0; half < 2; ++half) {
+            const int blk = 2 * c + half, nc = ncols_of(blk);
+            for (int j = warp; j < nc; j += nwarps) {
+                double* dst = M + (size_t)(blk * bs + j) * ld;
+                const double* src = xs + (size_t)(half * bs + j) * rpad;
+                for (int i = lane; i < rows_all; i += 32) dst[i] = src[i];
+            }
+        }
     }
     if (c == 0 && threadIdx.x == 0) *sweeps_out = done;
 }
@@ -409,7 +445,7 @@ static bool jacobi_sweeps_block(gsi_ctx* ctx, double* M, int64_t ld, int rows_do
     // rows per lane held in registers: 2 / 4 / 8 (then the column pitch is 32 * NR, zero padded); 0: streamed
     int NR = rows_all <= 64 ? 2 : (rows_all <= 128 && wpc <= 16) ? 4 : (rows_all <= 256 && wpc <= 16) ? 8 : 0;
     const int rpad = NR > 0 ? 32 * NR : (rows_all + 3) / 4 * 4 + 4;      // column pitch in shared memory
-    const size_t smem = (size_t)2 * bs * rpad * sizeof(double);
+    const size_t smem = (size_t)2 * 2 * bs * rpad * sizeof(double);     // two tiles (double-buffered exchange)
     if (smem > (size_t)200 * 1024) return false;
     const void* kfn = NR == 2 ? (const void*)jacobi_block_kernel<2> : NR == 4 ? (const void*)jacobi_block_kernel<4>
                     : NR == 8 ? (const void*)jacobi_block_kernel<8> : (const void*)jacobi_block_kernel<0>;
