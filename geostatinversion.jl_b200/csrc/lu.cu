@@ -53,7 +53,8 @@ constexpr int LU_THREADS = 256;
 constexpr int LU_WARPS = LU_THREADS / 32;
 constexpr int LP_THREADS = 512;      // panel kernel: 16 warps, 4 lanes per row -> 128 rows per pass
 constexpr int LP_WARPS = LP_THREADS / 32;
-constexpr int LP_PITCH = 20;         // shared-memory row pitch (doubles): 4 lanes x 4 rows of a half-warp hit 16 distinct banks
+constexpr int LP_PITCH = 17;         // shared-memory row pitch (doubles), odd: the 32 rows a warp eliminates (one thread per row, same
+                                     // column) fall into distinct bank pairs
 
 struct Cand { double val; double idx; };   // idx = global row index (exact in a double)
 
@@ -303,11 +304,9 @@ __global__ void __launch_bounds__(LP_THREADS, 1) lu_panel_kernel(const LuPanelPa
     {
         unsigned long long key = 0ull;
         int row = 0x7fffffff;
-        if (sub == 0) {
-            for (int li = lfirst + rslot; li < nown; li += LP_THREADS / 4) {
-                const unsigned long long kk = lp_key(rowp(li)[0]);
-                if (kk > key) { key = kk; row = (int)(r0 + li); }
-            }
+        for (int li = lfirst + tid; li < nown; li += LP_THREADS) {
+            const unsigned long long kk = lp_key(rowp(li)[0]);
+            if (kk > key) { key = kk; row = (int)(r0 + li); }
         }
         publish(p.ps, 0, key, row);
     }
@@ -377,17 +376,11 @@ __global__ void __launch_bounds__(LP_THREADS, 1) lu_panel_kernel(const LuPanelPa
         }
         // LAPACK dgetf2: multiply by the reciprocal when |pivot| >= sfmin, divide otherwise; a zero pivot leaves the column
         const int mode = pivot == 0.0 ? 2 : (fabs(pivot) >= 2.2250738585072014e-308 ? 0 : 1);
-        // my four columns: the pivot row's entries, and which of them this step updates
-        double pr[4];
-        bool act[4];
+        // the pivot row's entries right of column c (0 elsewhere: those columns are left alone)
+        double pr[LU_PB];
 #pragma unroll
-        for (int cc = 0; cc < 4; ++cc) {
-            const int j = sub + 4 * cc;
-            act[cc] = j > c && j < pb;
-            pr[cc] = act[cc] ? prow[j] : 0.0;
-        }
-        const int ncc = (c + 1) >> 2, nsub = (c + 1) & 3;                    // the next column lives in lane sub == nsub, slot ncc
-        const bool has_next = (c + 1 < pb) && sub == nsub;
+        for (int j = 0; j < LU_PB; ++j) pr[j] = (j > c && j < pb) ? prow[j] : 0.0;
+        const bool has_next = c + 1 < pb;
         // ---- row interchange inside the panel, each row by its owner
         if (piv != k) {
             if (tid < pb) {
@@ -397,39 +390,34 @@ __global__ void __launch_bounds__(LP_THREADS, 1) lu_panel_kernel(const LuPanelPa
             }
             __syncthreads();
         }
-        // ---- elimination of my rows below k, candidates for column k+1
+        // ---- elimination of my rows below k, candidates for column k+1: ONE THREAD PER ROW (all 16 panel columns
+        //      of a row in one thread: ~60 instructions per row instead of ~100 per quarter row with four lanes per
+        //      row -- the panel kernels are bound by the instruction stream of a warp, not by shared-memory bandwidth)
         unsigned long long bkey = 0ull;
         int brow = 0x7fffffff;
-        // (warp-uniform trip counts and full-mask warp primitives: partial-mask variants compile to divergence-safe
-        //  sequences that cost more than the predicated tail iteration)
-        auto eliminate_row = [&](double* row, int li, bool valid) {
-            const double a = valid ? row[c] : 0.0;
-            __syncwarp();                                   // all four lanes of a row have read a before lane 0 replaces it
+        auto eliminate_row = [&](double* row, int li) {
+            const double a = row[c];
             const double m = mode == 0 ? a * rpiv : (mode == 1 ? a / pivot : a);
-            if (valid && sub == 0) row[c] = m;
+            row[c] = m;
             double nextv = 0.0;
 #pragma unroll
-            for (int cc = 0; cc < 4; ++cc) {
-                if (valid && act[cc]) {
-                    const double v = fma(-m, pr[cc], row[sub + 4 * cc]);
-                    row[sub + 4 * cc] = v;
-                    if (cc == ncc) nextv = v;
+            for (int j = 1; j < LU_PB; ++j) {
+                if (j > c && j < pb) {                      // (uniform over the block)
+                    const double v = fma(-m, pr[j], row[j]);
+                    row[j] = v;
+                    if (j == c + 1) nextv = v;
                 }
             }
-            if (valid && has_next) {
+            if (has_next) {
                 const unsigned long long kk = lp_key(nextv);
                 if (kk > bkey) { bkey = kk; brow = (int)(r0 + li); }
             }
         };
         const int lstart = (k + 1 > r0) ? (int)((k + 1 - r0 < nown) ? k + 1 - r0 : nown) : 0;
-        for (int base = lstart; base < nres; base += LP_THREADS / 4) {       // rows resident in shared memory
-            const int li = base + rslot;
-            eliminate_row(sm + (size_t)(li < nres ? li : 0) * LP_PITCH, li, li < nres);
-        }
-        for (int base = (nres > lstart ? nres : lstart); base < nown; base += LP_THREADS / 4) {   // overflow rows, in place
-            const int li = base + rslot;
-            eliminate_row(Ypan + (r0 + (li < nown ? li : 0)) * ld, li, li < nown);
-        }
+        for (int li = lstart + tid; li < nres; li += LP_THREADS)             // rows resident in shared memory
+            eliminate_row(sm + (size_t)li * LP_PITCH, li);
+        for (int li = (nres > lstart ? nres : lstart) + tid; li < nown; li += LP_THREADS)   // overflow rows, in place
+            eliminate_row(Ypan + (r0 + li) * ld, li);
         if (k + 1 < p.pe) publish(k + 1, c + 1, bkey, brow);
     }
     __syncthreads();

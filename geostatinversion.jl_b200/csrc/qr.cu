@@ -175,12 +175,12 @@ qr_update_kernel(double* __restrict__ Y, int64_t ld, int64_t n, int ps, int pe, 
 // ----------------------------------------------------------------------------- panel driver
 // One cooperative launch per panel [ps, pe).  CTA b owns
 // rows [b*R, (b+1)*R) of Y; its rows >= ps are active; the first `cap` owned rows live in shared
-// memory (pitch QPK_PITCH: the 4 lanes x 4 rows of a half-warp hit 16 distinct banks), the rest
+// memory (pitch QPK_PITCH), the rest
 // is worked on in place.  Per column step every CTA publishes ONE record (panel_xch.cuh), then the grid barrier:
 //     [ its 16 partial dot products of column k with the panel columns, row k's 16 panel entries (owner only) ].
 constexpr int QPK_THREADS = 512;
 constexpr int QPK_WARPS = QPK_THREADS / 32;
-constexpr int QPK_PITCH = 20;
+constexpr int QPK_PITCH = 17;        // odd: the 32 rows a warp updates (one thread per row, same column) fall into distinct bank pairs
 constexpr int QPK_SLICES = QPK_THREADS / QB;      // 32 slices of the cross-CTA reduction
 
 struct QrPanelParams {
@@ -195,12 +195,43 @@ struct QrPanelParams {
 
 // CL = 0: cooperative grid, records in global memory; CL = 1: the launch is one thread-block cluster,
 // records pushed into every CTA's shared memory (panel_xch.cuh).
+// Sum of ps[0..15] over the 32 lanes of a warp in 16 shuffle-adds (transposing butterfly: every stage halves the
+// values a lane carries): afterwards lane L holds the warp total of column qr_col_of_lane(L) (each column in two
+// lanes).  Fixed order, so deterministic.
+__device__ __forceinline__ int qr_col_of_lane(int lane) {
+    return ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
+}
+__device__ __forceinline__ double qr_warp_reduce16(const double (&ps)[QB], int lane) {
+    double h8[8], h4[4], h2[2];
+    const bool u16 = lane & 16, u8 = lane & 8, u4 = lane & 4, u2 = lane & 2;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const double send = u16 ? ps[i] : ps[i + 8], keep = u16 ? ps[i + 8] : ps[i];
+        h8[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const double send = u8 ? h8[i] : h8[i + 4], keep = u8 ? h8[i + 4] : h8[i];
+        h4[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+    }
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+        const double send = u4 ? h4[i] : h4[i + 2], keep = u4 ? h4[i + 2] : h4[i];
+        h2[i] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+    }
+    const double send = u2 ? h2[0] : h2[1], keep = u2 ? h2[1] : h2[0];
+    double h = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+    h += __shfl_xor_sync(0xffffffffu, h, 1);
+    return h;
+}
+
 template <int CL>
 __global__ void __launch_bounds__(QPK_THREADS, 1) qr_panel_kernel(const QrPanelParams p) {
     extern __shared__ double sm[];                 // [cap][QPK_PITCH]
     __shared__ double s_xrec[CL ? 2 * kPxchClusterMax * kPxchRec : 1];   // CL = 1: everybody's records, by parity
     __shared__ double s_red[QPK_SLICES][QB];
     __shared__ double s_wpart[QPK_WARPS][QB];
+    __shared__ double s_twv[QPK_WARPS][QB];        // CL = 1: tw of the column step, per warp
     __shared__ double s_g[QB], s_tw[QB];
     __shared__ double s_scale;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, sub = lane & 3, rslot = tid >> 2;
@@ -252,13 +283,11 @@ __global__ void __launch_bounds__(QPK_THREADS, 1) qr_panel_kernel(const QrPanelP
 
     // block reduction of the lanes' psum[cc] (panel column sub + 4cc) -> my record of column step c;
     // the owner of row `col` also publishes that row
-    auto publish = [&](int col, int c, double (&psum)[4]) {
+    auto publish = [&](int col, int c, const double (&psum)[QB]) {
         const int par = c & 1;
-#pragma unroll
-        for (int cc = 0; cc < 4; ++cc) {
-            double v = psum[cc];
-            for (int o = 4; o < 32; o <<= 1) v += __shfl_xor_sync(0xffffffffu, v, o);   // over the 8 row slots
-            if (lane < 4) s_wpart[warp][sub + 4 * cc] = v;
+        {
+            const double v = qr_warp_reduce16(psum, lane);                              // over the 32 rows of the warp
+            if ((lane & 1) == 0) s_wpart[warp][qr_col_of_lane(lane)] = v;
         }
         __syncthreads();                                   // also: all rows of this CTA are up to date
         if (CL) {
@@ -284,17 +313,17 @@ __global__ void __launch_bounds__(QPK_THREADS, 1) qr_panel_kernel(const QrPanelP
         barrier();                                         // every CTA's record of this column step is visible
     };
 
-    // ---- dots of the first panel column with the panel columns, rows > ps
+    // ---- dots of the first panel column with the panel columns, rows > ps (one thread per row)
     {
-        double psum[4] = {0.0, 0.0, 0.0, 0.0};
-        for (int li = first_local((int64_t)p.ps + 1) + rslot; li < nown; li += QPK_THREADS / 4) {
+        double psum[QB];
+#pragma unroll
+        for (int j = 0; j < QB; ++j) psum[j] = 0.0;
+        for (int li = first_local((int64_t)p.ps + 1) + tid; li < nown; li += QPK_THREADS) {
             const double* row = rowp(li);
             const double y0 = row[0];
 #pragma unroll
-            for (int c = 0; c < 4; ++c) {
-                const int j = sub + 4 * c;
-                if (j < pb) psum[c] = fma(y0, row[j], psum[c]);
-            }
+            for (int j = 0; j < QB; ++j)
+                if (j < pb) psum[j] = fma(y0, row[j], psum[j]);
         }
         publish(p.ps, 0, psum);
     }
@@ -306,7 +335,7 @@ __global__ void __launch_bounds__(QPK_THREADS, 1) qr_panel_kernel(const QrPanelP
         const bool own_k = (k >= r0 && k < r1);
         const double alpha = rec_rd(par, owner_k, QB + c);                 // (issued together with the partials)
         double scale;
-        double twv[4];                                                     // tw[j] = tau * (v' Y[:, j]) of my four columns
+        double twv[QB];                                                    // tw[j] = tau * (v' Y[:, j]), 0 for j <= c
         if (CL) {
             // ---- every WARP sums the G partials of column `lane` (CTA order) and derives the Householder scalars
             //      (dlarfg) for itself: no block barrier between the cluster barrier and the update of the rows
@@ -331,8 +360,11 @@ __global__ void __launch_bounds__(QPK_THREADS, 1) qr_panel_kernel(const QrPanelP
                 else if (lane == c) rowp((int)(k - r0))[c] = beta;
             }
             if (tid == 0 && b == 0) p.taus[k] = tau;
+            if (lane < QB) s_twv[warp][lane] = t;
+            __syncwarp();
 #pragma unroll
-            for (int cc = 0; cc < 4; ++cc) twv[cc] = __shfl_sync(0xffffffffu, t, sub + 4 * cc);
+            for (int j = 0; j < QB; ++j) twv[j] = s_twv[warp][j];
+            __syncwarp();
         } else {
             const double ykj_mine = (tid < pb) ? rec_rd(par, owner_k, QB + tid) : 0.0;
             // ---- every CTA reduces the G partials in the same fixed order (all loads in flight before the first add)
@@ -389,53 +421,40 @@ __global__ void __launch_bounds__(QPK_THREADS, 1) qr_panel_kernel(const QrPanelP
             __syncthreads();
             scale = s_scale;
 #pragma unroll
-            for (int cc = 0; cc < 4; ++cc) twv[cc] = (sub + 4 * cc < pb) ? s_tw[sub + 4 * cc] : 0.0;
+            for (int j = 0; j < QB; ++j) twv[j] = (j < pb) ? s_tw[j] : 0.0;
         }
-        // ---- rows i > k: v_i = scale * Y[i,k]; Y[i,j] -= v_i * tw[j]; dots of column k+1 (rows > k+1)
-        double psum[4] = {0.0, 0.0, 0.0, 0.0};
+        // ---- rows i > k: v_i = scale * Y[i,k]; Y[i,j] -= v_i * tw[j]; dots of column k+1 (rows > k+1).
+        //      ONE THREAD PER ROW: the 16 panel columns of a row, the new column-(k+1) entry and its 16 products stay
+        //      in one thread (no shuffles, ~70 instructions per row instead of ~100 per quarter row).
+        double psum[QB];
+#pragma unroll
+        for (int j = 0; j < QB; ++j) psum[j] = 0.0;
         const int lstart = first_local((int64_t)k + 1);
-        const int slot = c + 1;                              // panel slot of the next column
         const int li_top = (k + 1 >= r0 && k + 1 < r1) ? (int)(k + 1 - r0) : -1;     // row k+1 itself takes no part in the dots
-        const int src_lane = (lane & ~3) | (slot & 3);
-        bool act[4];
+        auto update_row = [&](double* row, int li) {
+            double nv[QB];
+            const double v = scale * row[c];
+            row[c] = v;
+            double ynext = 0.0;
 #pragma unroll
-        for (int cc = 0; cc < 4; ++cc) act[cc] = (sub + 4 * cc > c) && (sub + 4 * cc < pb);
-        const bool has_c = (sub == (c & 3));                 // my slot (c >> 2) is column c itself
-        // (warp-uniform trip counts and full-mask warp primitives: partial-mask variants compile to divergence-safe
-        //  sequences that cost more than the predicated tail iteration)
-        auto update_row = [&](double* row, int li, bool valid) {
-            double nv[4] = {0.0, 0.0, 0.0, 0.0};
-            const double a = valid ? row[c] : 0.0;
-            __syncwarp();                                   // all four lanes of a row have read a before it is replaced
-            const double v = scale * a;
-#pragma unroll
-            for (int cc = 0; cc < 4; ++cc) {
-                if (valid && act[cc]) {
-                    nv[cc] = row[sub + 4 * cc] - v * twv[cc];
-                    row[sub + 4 * cc] = nv[cc];
-                } else if (valid && has_c && cc == (c >> 2)) {
-                    nv[cc] = v;
-                    row[c] = v;
+            for (int j = 0; j < QB; ++j) {
+                nv[j] = 0.0;
+                if (j == c) nv[j] = v;
+                if (j > c && j < pb) {                      // (uniform over the block)
+                    nv[j] = row[j] - v * twv[j];
+                    row[j] = nv[j];
+                    if (j == c + 1) ynext = nv[j];
                 }
             }
-            double mine = 0.0;
+            if (li != li_top) {
 #pragma unroll
-            for (int cc = 0; cc < 4; ++cc)
-                if (cc == (slot >> 2)) mine = nv[cc];
-            const double ynext = __shfl_sync(0xffffffffu, mine, src_lane);
-            if (valid && li != li_top) {
-#pragma unroll
-                for (int cc = 0; cc < 4; ++cc) psum[cc] = fma(ynext, nv[cc], psum[cc]);
+                for (int j = 0; j < QB; ++j) psum[j] = fma(ynext, nv[j], psum[j]);
             }
         };
-        for (int base = lstart; base < nres; base += QPK_THREADS / 4) {      // rows resident in shared memory
-            const int li = base + rslot;
-            update_row(sm + (size_t)(li < nres ? li : 0) * QPK_PITCH, li, li < nres);
-        }
-        for (int base = (nres > lstart ? nres : lstart); base < nown; base += QPK_THREADS / 4) {   // overflow rows, in place
-            const int li = base + rslot;
-            update_row(Ypan + (r0 + (li < nown ? li : 0)) * ld, li, li < nown);
-        }
+        for (int li = lstart + tid; li < nres; li += QPK_THREADS)            // rows resident in shared memory
+            update_row(sm + (size_t)li * QPK_PITCH, li);
+        for (int li = (nres > lstart ? nres : lstart) + tid; li < nown; li += QPK_THREADS)   // overflow rows, in place
+            update_row(Ypan + (r0 + li) * ld, li);
         if (k + 1 < p.pe) publish(k + 1, c + 1, psum);
     }
     __syncthreads();
