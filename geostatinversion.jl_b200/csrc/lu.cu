@@ -416,8 +416,41 @@ __global__ void __launch_bounds__(LP_THREADS, 1) lu_panel_kernel(const LuPanelPa
         const int lstart = (k + 1 > r0) ? (int)((k + 1 - r0 < nown) ? k + 1 - r0 : nown) : 0;
         for (int li = lstart + tid; li < nres; li += LP_THREADS)             // rows resident in shared memory
             eliminate_row(sm + (size_t)li * LP_PITCH, li);
-        for (int li = (nres > lstart ? nres : lstart) + tid; li < nown; li += LP_THREADS)   // overflow rows, in place
-            eliminate_row(Ypan + (r0 + li) * ld, li);
+        // rows beyond the shared-memory capacity (iterates of more than ~1690 rows per SM, e.g. 10^6 rows), in place in
+        // global memory: 16 LANES PER ROW, lane = column, so that a row is one coalesced 128-byte access (one thread
+        // per row would touch 32 lines per instruction: the 10^6-row LU took 87 ms instead of 25)
+        {
+            const int col = lane & 15, hw = lane >> 4;
+            const bool upd = col > c && col < pb;
+            const double prj = upd ? prow[col] : 0.0;
+            const int ostart = nres > lstart ? nres : lstart;
+            constexpr int UNR = 8;                          // row pairs in flight per warp (the loads are the latency)
+            for (int base = ostart + 2 * warp; base < nown; base += 2 * LP_WARPS * UNR) {      // warp-uniform trip count
+                double x[UNR];
+#pragma unroll
+                for (int u = 0; u < UNR; ++u) {
+                    const int li = base + u * 2 * LP_WARPS + hw;
+                    x[u] = (li < nown && col < pb) ? Ypan[(r0 + li) * ld + col] : 0.0;
+                }
+#pragma unroll
+                for (int u = 0; u < UNR; ++u) {
+                    const int li = base + u * 2 * LP_WARPS + hw;
+                    const bool valid = li < nown;
+                    const double a = __shfl_sync(0xffffffffu, x[u], (lane & 16) | c);
+                    const double m = mode == 0 ? a * rpiv : (mode == 1 ? a / pivot : a);
+                    double* row = Ypan + (r0 + (valid ? li : ostart)) * ld;
+                    if (valid && col == c) row[col] = m;
+                    if (valid && upd) {
+                        const double v = fma(-m, prj, x[u]);
+                        row[col] = v;
+                        if (col == c + 1) {
+                            const unsigned long long kk = lp_key(v);
+                            if (kk > bkey) { bkey = kk; brow = (int)(r0 + li); }
+                        }
+                    }
+                }
+            }
+        }
         if (k + 1 < p.pe) publish(k + 1, c + 1, bkey, brow);
     }
     __syncthreads();

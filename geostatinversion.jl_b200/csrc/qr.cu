@@ -283,11 +283,15 @@ __global__ void __launch_bounds__(QPK_THREADS, 1) qr_panel_kernel(const QrPanelP
 
     // block reduction of the lanes' psum[cc] (panel column sub + 4cc) -> my record of column step c;
     // the owner of row `col` also publishes that row
-    auto publish = [&](int col, int c, const double (&psum)[QB]) {
+    // psum: per-thread dot products of the rows in shared memory; ovsum: lane j < 16 holds the warp's dot product of
+    // column j over its rows in global memory
+    auto publish = [&](int col, int c, const double (&psum)[QB], double ovsum) {
         const int par = c & 1;
         {
             const double v = qr_warp_reduce16(psum, lane);                              // over the 32 rows of the warp
             if ((lane & 1) == 0) s_wpart[warp][qr_col_of_lane(lane)] = v;
+            __syncwarp();
+            if (lane < QB) s_wpart[warp][lane] += ovsum;
         }
         __syncthreads();                                   // also: all rows of this CTA are up to date
         if (CL) {
@@ -313,19 +317,41 @@ __global__ void __launch_bounds__(QPK_THREADS, 1) qr_panel_kernel(const QrPanelP
         barrier();                                         // every CTA's record of this column step is visible
     };
 
-    // ---- dots of the first panel column with the panel columns, rows > ps (one thread per row)
+    // ---- dots of the first panel column with the panel columns, rows > ps (one thread per row in shared memory,
+    //      16 lanes per row for the rows in global memory)
     {
         double psum[QB];
 #pragma unroll
         for (int j = 0; j < QB; ++j) psum[j] = 0.0;
-        for (int li = first_local((int64_t)p.ps + 1) + tid; li < nown; li += QPK_THREADS) {
-            const double* row = rowp(li);
+        const int lstart = first_local((int64_t)p.ps + 1);
+        for (int li = lstart + tid; li < nres; li += QPK_THREADS) {
+            const double* row = sm + (size_t)li * QPK_PITCH;
             const double y0 = row[0];
 #pragma unroll
             for (int j = 0; j < QB; ++j)
                 if (j < pb) psum[j] = fma(y0, row[j], psum[j]);
         }
-        publish(p.ps, 0, psum);
+        double ovsum = 0.0;
+        {
+            const int col = lane & 15, hw = lane >> 4;
+            const int ostart = nres > lstart ? nres : lstart;
+            constexpr int UNR = 8;
+            for (int base = ostart + 2 * warp; base < nown; base += 2 * QPK_WARPS * UNR) {     // warp-uniform trip count
+                double x[UNR];
+#pragma unroll
+                for (int u = 0; u < UNR; ++u) {
+                    const int li = base + u * 2 * QPK_WARPS + hw;
+                    x[u] = (li < nown && col < pb) ? Ypan[(r0 + li) * ld + col] : 0.0;
+                }
+#pragma unroll
+                for (int u = 0; u < UNR; ++u) {
+                    const double y0 = __shfl_sync(0xffffffffu, x[u], lane & 16);
+                    ovsum = fma(y0, x[u], ovsum);                   // (rows past the end and columns >= pb contribute zeros)
+                }
+            }
+            ovsum += __shfl_xor_sync(0xffffffffu, ovsum, 16);
+        }
+        publish(p.ps, 0, psum, ovsum);
     }
 
     for (int k = p.ps; k < p.pe; ++k) {
@@ -423,6 +449,7 @@ __global__ void __launch_bounds__(QPK_THREADS, 1) qr_panel_kernel(const QrPanelP
 #pragma unroll
             for (int j = 0; j < QB; ++j) twv[j] = (j < pb) ? s_tw[j] : 0.0;
         }
+        auto twv_of = [&](int j) -> double { return CL ? s_twv[warp][j] : s_tw[j]; };   // tw[j] by a run-time column index
         // ---- rows i > k: v_i = scale * Y[i,k]; Y[i,j] -= v_i * tw[j]; dots of column k+1 (rows > k+1).
         //      ONE THREAD PER ROW: the 16 panel columns of a row, the new column-(k+1) entry and its 16 products stay
         //      in one thread (no shuffles, ~70 instructions per row instead of ~100 per quarter row).
@@ -453,9 +480,38 @@ __global__ void __launch_bounds__(QPK_THREADS, 1) qr_panel_kernel(const QrPanelP
         };
         for (int li = lstart + tid; li < nres; li += QPK_THREADS)            // rows resident in shared memory
             update_row(sm + (size_t)li * QPK_PITCH, li);
-        for (int li = (nres > lstart ? nres : lstart) + tid; li < nown; li += QPK_THREADS)   // overflow rows, in place
-            update_row(Ypan + (r0 + li) * ld, li);
-        if (k + 1 < p.pe) publish(k + 1, c + 1, psum);
+        // rows beyond the shared-memory capacity, in place in global memory: 16 LANES PER ROW, lane = column (one
+        // coalesced 128-byte access per row); the lane accumulates the dot product of its own column
+        double ovsum = 0.0;
+        {
+            const int col = lane & 15, hw = lane >> 4;
+            const bool upd = col > c && col < pb;
+            const double twj = upd ? twv_of(col) : 0.0;
+            const int ostart = nres > lstart ? nres : lstart;
+            constexpr int UNR = 8;                          // row pairs in flight per warp (the loads are the latency)
+            for (int base = ostart + 2 * warp; base < nown; base += 2 * QPK_WARPS * UNR) {     // warp-uniform trip count
+                double x[UNR];
+#pragma unroll
+                for (int u = 0; u < UNR; ++u) {
+                    const int li = base + u * 2 * QPK_WARPS + hw;
+                    x[u] = (li < nown && col < pb) ? Ypan[(r0 + li) * ld + col] : 0.0;
+                }
+#pragma unroll
+                for (int u = 0; u < UNR; ++u) {
+                    const int li = base + u * 2 * QPK_WARPS + hw;
+                    const bool valid = li < nown;
+                    const double v = scale * __shfl_sync(0xffffffffu, x[u], (lane & 16) | c);
+                    double nvj = 0.0;
+                    if (col == c) nvj = v;
+                    if (upd) nvj = x[u] - v * twj;
+                    if (valid && (upd || col == c)) Ypan[(r0 + li) * ld + col] = nvj;
+                    const double ynext = __shfl_sync(0xffffffffu, nvj, (lane & 16) | ((c + 1) & 15));
+                    if (valid && li != li_top && c + 1 < pb) ovsum = fma(ynext, nvj, ovsum);
+                }
+            }
+            ovsum += __shfl_xor_sync(0xffffffffu, ovsum, 16);          // both half-warps: lane j < 16 holds column j
+        }
+        if (k + 1 < p.pe) publish(k + 1, c + 1, psum, ovsum);
     }
     __syncthreads();
     for (int li = lfirst + rslot; li < nres; li += QPK_THREADS / 4) {

@@ -25,7 +25,8 @@ def _with_option(ctx, name, value, fn):
 # shared memory holds (overflow rows worked on in place: n > 148 * 1432)
 LU_SHAPES = [(64, 8), (40, 33), (300, 17), (1000, 60), (5000, 110), (20000, 210), (777, 256), (2049, 16),
              (230000, 40), (3000, 300), (1500, 520),      # the last two: iterates wider than 256 columns
-             (10000, 110), (25088, 48), (26900, 20), (27100, 20)]   # one cluster of 16 CTAs; rows beyond its shared memory; just past it
+             (10000, 110), (25088, 48), (26900, 20), (27100, 20),   # one cluster of 16 CTAs; rows beyond its shared memory; just past it
+             (300000, 20)]                                          # cooperative grid with rows beyond the SMs' shared memory
 
 
 @pytest.mark.parametrize("n,l", LU_SHAPES)
@@ -106,7 +107,7 @@ def test_lu_nan_propagates(gsi):
 
 
 QR_SHAPES = [(64, 8), (1000, 60), (20000, 210), (300, 256), (5000, 33), (2049, 16), (230000, 24), (3000, 300), (1500, 520),
-             (10000, 110), (25088, 48), (27100, 20)]
+             (10000, 110), (25088, 48), (26900, 20), (27100, 20), (300000, 20)]
 
 
 @pytest.mark.parametrize("n,l", QR_SHAPES)
