@@ -189,6 +189,7 @@ struct QrPanelParams {
     unsigned int* bar;              // CL = 0: barrier counters (panel_xch.cuh)
     unsigned int bar_base;          //         barriers of this factorisation before this launch
     double* taus;
+    double* T;                      // out: the panel's T factor (QB x QB, column-major, upper triangular), written by CTA 0
     int64_t R;
     int cap;
 };
@@ -234,6 +235,8 @@ __global__ void __launch_bounds__(QPK_THREADS, 1) qr_panel_kernel(const QrPanelP
     __shared__ double s_twv[QPK_WARPS][QB];        // CL = 1: tw of the column step, per warp
     __shared__ double s_g[QB], s_tw[QB];
     __shared__ double s_scale;
+    __shared__ double s_T[QB][QB + 1], s_tau[QB], s_z[QB];   // T factor of the panel, built column by column (warp 0)
+    __shared__ double s_vrow[QB];                  // row ps + c of the panel as published for column step c (kept for the T column)
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, sub = lane & 3, rslot = tid >> 2;
     const int G = (int)gridDim.x, b = (int)blockIdx.x;       // CL = 1: the grid is one cluster
     const int pb = p.pe - p.ps;
@@ -317,6 +320,25 @@ __global__ void __launch_bounds__(QPK_THREADS, 1) qr_panel_kernel(const QrPanelP
         barrier();                                         // every CTA's record of this column step is visible
     };
 
+    // T factor (dlarft) without a separate pass: while the rows are updated for reflector c, the slots j < c of the
+    // dot-product record (unused by the factorisation) accumulate z_c[j] = sum_{i > k} V[i, j] * v_c[i]; with the unit
+    // entry of v_c this gives V[:, 0:c]' v_c, and T[0:c, c] = -tau_c * T[0:c, 0:c] * z_c.  Warp 0, lane m holding the
+    // reduced slot m; cprev = c - 1 at the start of step c (and once more after the last step).  Row ps + cprev
+    // was saved in s_vrow during step cprev (its record may already be overwritten: records live for one step).
+    auto build_T_column = [&](int cprev, double g_lane) {
+        if (lane < cprev) s_z[lane] = g_lane + s_vrow[lane];                             // + V[ps + cprev, m] * 1
+        __syncwarp();
+        const double tau = s_tau[cprev];
+        if (lane < cprev) {
+            double zz = 0.0;
+            for (int m = lane; m < cprev; ++m) zz += s_T[lane][m] * s_z[m];
+            s_T[lane][cprev] = -tau * zz;
+        } else if (lane == cprev) {
+            s_T[cprev][cprev] = tau;
+        }
+        __syncwarp();
+    };
+
     // ---- dots of the first panel column with the panel columns, rows > ps (one thread per row in shared memory,
     //      16 lanes per row for the rows in global memory)
     {
@@ -370,6 +392,10 @@ __global__ void __launch_bounds__(QPK_THREADS, 1) qr_panel_kernel(const QrPanelP
             for (int q = 0; q < kPxchClusterMax; ++q)
                 if (q < G && lane < QB) gj += rec_rd(par, q, lane);
             const double ykj = (lane < pb) ? rec_rd(par, owner_k, QB + lane) : 0.0;
+            if (warp == 0) {
+                if (c >= 1) build_T_column(c - 1, gj);
+                if (lane < QB) s_vrow[lane] = ykj;
+            }
             const double xnorm2 = __shfl_sync(0xffffffffu, gj, c);
             double tau = 0.0, beta = alpha;
             scale = 0.0;
@@ -385,7 +411,10 @@ __global__ void __launch_bounds__(QPK_THREADS, 1) qr_panel_kernel(const QrPanelP
                 if (lane > c && lane < pb) rowp((int)(k - r0))[lane] = ykj - t;
                 else if (lane == c) rowp((int)(k - r0))[c] = beta;
             }
-            if (tid == 0 && b == 0) p.taus[k] = tau;
+            if (tid == 0) {
+                s_tau[c] = tau;
+                if (b == 0) p.taus[k] = tau;
+            }
             if (lane < QB) s_twv[warp][lane] = t;
             __syncwarp();
 #pragma unroll
@@ -416,6 +445,10 @@ __global__ void __launch_bounds__(QPK_THREADS, 1) qr_panel_kernel(const QrPanelP
                 s_g[tid] = s;
             }
             __syncthreads();
+            if (warp == 0) {
+                if (c >= 1) build_T_column(c - 1, lane < QB ? s_g[lane] : 0.0);
+                if (lane < QB) s_vrow[lane] = ykj_mine;      // (tid < pb holds row k's entry; 0 beyond)
+            }
             // ---- Householder scalars (dlarfg), redundantly in every CTA; tw[j] = tau * (v' Y[:, j])
             {
                 const double xnorm2 = s_g[c];
@@ -428,6 +461,7 @@ __global__ void __launch_bounds__(QPK_THREADS, 1) qr_panel_kernel(const QrPanelP
                 }
                 if (tid == 0) {
                     s_scale = sc;
+                    s_tau[c] = tau;
                     if (b == 0) p.taus[k] = tau;
                 }
                 if (tid < pb) {
@@ -466,6 +500,7 @@ __global__ void __launch_bounds__(QPK_THREADS, 1) qr_panel_kernel(const QrPanelP
 #pragma unroll
             for (int j = 0; j < QB; ++j) {
                 nv[j] = 0.0;
+                if (j < c) nv[j] = row[j];                  // reflector entries of the earlier columns (T factor)
                 if (j == c) nv[j] = v;
                 if (j > c && j < pb) {                      // (uniform over the block)
                     nv[j] = row[j] - v * twv[j];
@@ -473,10 +508,9 @@ __global__ void __launch_bounds__(QPK_THREADS, 1) qr_panel_kernel(const QrPanelP
                     if (j == c + 1) ynext = nv[j];
                 }
             }
-            if (li != li_top) {
+            const double ydot = (li != li_top) ? ynext : 0.0;
 #pragma unroll
-                for (int j = 0; j < QB; ++j) psum[j] = fma(ynext, nv[j], psum[j]);
-            }
+            for (int j = 0; j < QB; ++j) psum[j] = fma(j < c ? v : ydot, nv[j], psum[j]);
         };
         for (int li = lstart + tid; li < nres; li += QPK_THREADS)            // rows resident in shared memory
             update_row(sm + (size_t)li * QPK_PITCH, li);
@@ -506,12 +540,42 @@ __global__ void __launch_bounds__(QPK_THREADS, 1) qr_panel_kernel(const QrPanelP
                     if (upd) nvj = x[u] - v * twj;
                     if (valid && (upd || col == c)) Ypan[(r0 + li) * ld + col] = nvj;
                     const double ynext = __shfl_sync(0xffffffffu, nvj, (lane & 16) | ((c + 1) & 15));
-                    if (valid && li != li_top && c + 1 < pb) ovsum = fma(ynext, nvj, ovsum);
+                    if (valid && col < c) ovsum = fma(v, x[u], ovsum);                                  // T factor: V[i, col] * v_i
+                    else if (valid && li != li_top && c + 1 < pb) ovsum = fma(ynext, nvj, ovsum);
                 }
             }
             ovsum += __shfl_xor_sync(0xffffffffu, ovsum, 16);          // both half-warps: lane j < 16 holds column j
         }
-        if (k + 1 < p.pe) publish(k + 1, c + 1, psum, ovsum);
+        publish(k + 1 < p.pe ? k + 1 : -1, c + 1, psum, ovsum);      // (after the last column: only the T-factor sums)
+    }
+    // ---- last column of T, then the factor goes to global memory (CTA 0)
+    {
+        const int par = pb & 1;
+        double gl = 0.0;
+        if (CL) {
+#pragma unroll
+            for (int q = 0; q < kPxchClusterMax; ++q)
+                if (q < G && lane < QB) gl += rec_rd(par, q, lane);
+        } else {
+            const int j = tid % QB, slice = tid / QB;
+            double sacc = 0.0;
+            for (int q = slice; q < G; q += QPK_SLICES) sacc += rec_rd(par, q, j);
+            s_red[slice][j] = sacc;
+            __syncthreads();
+            if (lane < QB) {
+#pragma unroll
+                for (int sl = 0; sl < QPK_SLICES; ++sl) gl += s_red[sl][lane];
+            }
+        }
+        if (warp == 0) {
+            build_T_column(pb - 1, gl);
+            if (b == 0) {
+                for (int idx = lane; idx < QB * QB; idx += 32) {
+                    const int a = idx % QB, cc = idx / QB;
+                    p.T[cc * QB + a] = (a <= cc && cc < pb) ? s_T[a][cc] : 0.0;
+                }
+            }
+        }
     }
     __syncthreads();
     for (int li = lfirst + rslot; li < nres; li += QPK_THREADS / 4) {
@@ -830,6 +894,7 @@ void qr_thinQ_inplace(gsi_ctx* ctx, gsi_buf* Y, double* Rdev) {
         pp.recs = ctx->pxch;
         pp.bar = ctx->pbar; pp.bar_base = 0;
         pp.taus = taus;
+        pp.T = nullptr;
         pp.R = R; pp.cap = cap;
     };
     if (ctx->qr_panel == 1) panel_setup(1);
@@ -860,20 +925,20 @@ void qr_thinQ_inplace(gsi_ctx* ctx, gsi_buf* Y, double* Rdev) {
         double* T = Tall + (size_t)pi * QB * QB;
         bool done = false;
         if (pgrid > 0) {
-            pp.ps = ps; pp.pe = pe;
+            pp.ps = ps; pp.pe = pe; pp.T = T;
             cudaError_t e = panel_launch();
             if (e != cudaSuccess && pmode == 1) {
                 cudaGetLastError();            // the cluster could not be scheduled: cooperative grid from here on
                 panel_setup(0);
                 if (pgrid > 0) {
                     GSI_CUDA(cudaMemsetAsync(ctx->pbar, 0, kPbarBytes, st));
-                    pp.ps = ps; pp.pe = pe;
+                    pp.ps = ps; pp.pe = pe; pp.T = T;
                     e = panel_launch();
                 }
             }
             if (pgrid > 0 && e == cudaSuccess) {
                 count_launch(ctx);
-                pp.bar_base += (unsigned int)(pe - ps);     // one barrier per column step
+                pp.bar_base += (unsigned int)(pe - ps) + 1; // one barrier per column step + the T-factor exchange
                 done = true;
             } else {
                 cudaGetLastError();            // the grid could not be made co-resident: per-column driver
@@ -889,14 +954,17 @@ void qr_thinQ_inplace(gsi_ctx* ctx, gsi_buf* Y, double* Rdev) {
             GSI_CUDA(cudaGetLastError());
             count_launch(ctx, 1 + 2 * (pe - ps));
         }
-        // T factor: G = V'V (rows >= pe through the Gram kernel, top block inside qr_tbuild)
-        int nparts = 0, glp = 0;
         const int64_t rows_below = n - pe;
-        gram(ctx, Y->d + (int64_t)pe * Y->ld + ps, Y->ld, pe - ps, Y->d + (int64_t)pe * Y->ld + ps, Y->ld, pe - ps,
-             rows_below, gpart, nparts, glp);
-        qr_tbuild_kernel<<<1, QB * QB, 0, st>>>(Y->d, Y->ld, ps, pe, gpart, nparts, glp, taus, T);
-        GSI_CUDA(cudaGetLastError());
-        count_launch(ctx);
+        if (!done) {
+            // T factor: G = V'V (rows >= pe through the Gram kernel, top block inside qr_tbuild); the panel kernel
+            // delivers T itself
+            int nparts = 0, glp = 0;
+            gram(ctx, Y->d + (int64_t)pe * Y->ld + ps, Y->ld, pe - ps, Y->d + (int64_t)pe * Y->ld + ps, Y->ld, pe - ps,
+                 rows_below, gpart, nparts, glp);
+            qr_tbuild_kernel<<<1, QB * QB, 0, st>>>(Y->d, Y->ld, ps, pe, gpart, nparts, glp, taus, T);
+            GSI_CUDA(cudaGetLastError());
+            count_launch(ctx);
+        }
         if (pe < l) {
             // trailing update: Y2 <- (I - V T' V') Y2, in chunks of at most 256 trailing columns (wide iterates)
             for (int c0 = pe; c0 < l; c0 += kMaxCols) {
