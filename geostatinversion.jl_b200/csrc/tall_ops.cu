@@ -78,11 +78,20 @@ static void host_copy_rows(char* dst, const char* src, size_t nr, size_t width, 
     if (nt <= 1) { copy_range(0, total); return; }
     const size_t chunk = ((total + nt - 1) / nt + 4095) / 4096 * 4096;
     std::vector<std::thread> th;
+    th.reserve(nt);
+    size_t started_to = chunk < total ? chunk : total;          // bytes [chunk, started_to) are with helper threads
     for (size_t t = 1; t < nt; ++t) {
         const size_t b0 = t * chunk, b1 = (b0 + chunk < total) ? b0 + chunk : total;
-        if (b0 < total) th.emplace_back(copy_range, b0, b1);
+        if (b0 >= total) break;
+        try {
+            th.emplace_back(copy_range, b0, b1);
+        } catch (...) {
+            break;                                              // no more threads to be had: this thread copies the rest
+        }
+        started_to = b1;
     }
     copy_range(0, chunk < total ? chunk : total);
+    if (started_to < total) copy_range(started_to, total);
     for (auto& x : th) x.join();
 }
 
