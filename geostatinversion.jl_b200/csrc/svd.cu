@@ -226,8 +226,8 @@ template <int NR>
 __device__ __forceinline__ int jb_rotate_pair(double* __restrict__ mp, double* __restrict__ mq, int rows_dot, int rows_all,
                                               double tol, int lane) {
     double aa = 0.0, bb = 0.0, gg = 0.0, cs, sn;
-    if (NR > 0) {
-        double x[NR > 0 ? NR : 1], y[NR > 0 ? NR : 1];
+    if constexpr (NR > 0) {
+        double x[NR], y[NR];
 #pragma unroll
         for (int k = 0; k < NR; ++k) { x[k] = mp[lane + 32 * k]; y[k] = mq[lane + 32 * k]; }
 #pragma unroll
@@ -243,17 +243,18 @@ __device__ __forceinline__ int jb_rotate_pair(double* __restrict__ mp, double* _
             mq[lane + 32 * k] = ny;
         }
         return 1;
+    } else {
+        for (int i = lane; i < rows_dot; i += 32) jacobi_acc(mp[i], mq[i], aa, bb, gg);
+        aa = warp_sum(aa); bb = warp_sum(bb); gg = warp_sum(gg);
+        if (!jacobi_angle(aa, bb, gg, tol, cs, sn)) return 0;
+        for (int i = lane; i < rows_all; i += 32) {
+            double nx, ny;
+            jacobi_rot(cs, sn, mp[i], mq[i], nx, ny);
+            mp[i] = nx;
+            mq[i] = ny;
+        }
+        return 1;
     }
-    for (int i = lane; i < rows_dot; i += 32) jacobi_acc(mp[i], mq[i], aa, bb, gg);
-    aa = warp_sum(aa); bb = warp_sum(bb); gg = warp_sum(gg);
-    if (!jacobi_angle(aa, bb, gg, tol, cs, sn)) return 0;
-    for (int i = lane; i < rows_all; i += 32) {
-        double nx, ny;
-        jacobi_rot(cs, sn, mp[i], mq[i], nx, ny);
-        mp[i] = nx;
-        mq[i] = ny;
-    }
-    return 1;
 }
 
 // blockDim = 32 * max(bs, 2): warp w owns cross pair w of an inner round.

@@ -52,6 +52,10 @@ def test_sass_uses_fp64_tensor_cores_and_tma():
     sass = subprocess.run(["/usr/local/cuda/bin/cuobjdump", "-sass", LIB], capture_output=True, text=True).stdout
     assert "DMMA.8x8x4" in sass
     assert "UTMALDG" in sass and "UBLKCP" in sass
+    # thread-block-cluster kernels (short-iterate panel transport, block Jacobi): hardware cluster barrier;
+    # warp arg-max of the pivot search by redux.sync
+    assert "UCGABAR_ARV" in sass and "UCGABAR_WAIT" in sass
+    assert "REDUX" in sass
     assert "sm_100a" in subprocess.run(["/usr/local/cuda/bin/cuobjdump", "-lelf", LIB], capture_output=True,
                                        text=True).stdout
 
