@@ -126,8 +126,10 @@ function pinnedmatrix(ctx::Context, rows::Integer, cols::Integer)
 end
 freepinned(ctx::Context, A::Matrix{Float64}) = check(ccall((:gsi_host_free, LIB), Int32, (Ptr{Cvoid}, Ptr{Cvoid}), ctx.h, pointer(A)))
 
-# A TALL device iterate holds at most 256 columns; wider host matrices go through in passes.
+# One product pass handles at most 256 columns; wider host matrices go through in passes.  A TALL device
+# iterate itself may be up to 1024 columns wide (the library runs its products in 256-column chunks).
 const MAXCOLS = 256
+const MAXWIDECOLS = 1024
 
 abstract type Operator end
 # `rows` = this worker's block of global rows (all rows on a single-GPU context)
@@ -411,7 +413,7 @@ end
 splitR(R::AbstractMatrix, nobs) = (nothing, Matrix{Float64}(R))
 
 function xistodevice(ctx::Context, xis::Vector{Vector{Float64}})
-	length(xis) + 3 <= MAXCOLS || throw(ArgumentError("at most $(MAXCOLS - 3) xis (a device iterate holds 256 columns)"))
+	length(xis) + 3 <= MAXWIDECOLS || throw(ArgumentError("at most $(MAXWIDECOLS - 3) xis (the batch of K+3 parameter vectors is one device iterate of at most 1024 columns)"))
 	Zk = reduce(hcat, xis)
 	return upload!(DeviceMatrix(ctx, GSI_LAYOUT_TALL, size(Zk)...), Zk)
 end
